@@ -1,0 +1,61 @@
+"""Build the small graph fixtures under tests/golden/ from the reference's data files.
+
+Run in the build container only (needs /root/reference):  python scripts/make_fixtures.py
+The preprocessing mirrors Tests/test_unweighted_break.m:45-53 (symmetrise with spones(A+A'),
+drop self-loops, largest connected component) and Tests/test_weighted_sinh_lbfgs.m:48 (A/max(A)).
+Each fixture is a CSR triple (indptr, indices, data) + n in one .npz (a few kB each).
+"""
+import os
+
+import numpy as np
+import scipy.io as sio
+import scipy.sparse as sp
+from scipy.sparse.csgraph import connected_components
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def save(name, A):
+    A = sp.csr_matrix(A).astype(np.float64)
+    A.sort_indices()
+    A.eliminate_zeros()
+    assert (A != A.T).nnz == 0
+    np.savez_compressed(os.path.join(OUT, "graph_%s.npz" % name), n=A.shape[0], indptr=A.indptr.astype(np.int64),
+                        indices=A.indices.astype(np.int64), data=A.data)
+    print(name, A.shape[0], A.nnz)
+
+
+def lcc(A):
+    _, lab = connected_components(A, directed=False)
+    big = np.argmax(np.bincount(lab))     # first largest label, as the reference's loop (:163-167)
+    idx = np.where(lab == big)[0]
+    return A[idx][:, idx]
+
+
+def unweighted(A):
+    A = sp.csr_matrix(A).astype(np.float64)
+    A = A + A.T
+    A.data[:] = 1.0
+    A.setdiag(0)
+    A.eliminate_zeros()
+    return lcc(A.tocsr())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    m = sio.loadmat(os.path.join(REF, "MIOBI Codes", "dt_oregon.mat"), spmatrix=True)
+    for k in ("A0", "A1", "A8"):
+        save("oregon_%s" % k, m[k])
+    for k in ("Anaheim", "Barcelona", "Rome"):
+        p = sio.loadmat(os.path.join(REF, "datasets_paper", "Transport", k + ".mat"), spmatrix=True)
+        save("transport_%s" % k, unweighted(p["Problem"]["A"][0, 0]))
+    v = sio.loadmat(os.path.join(REF, "datasets_paper", "voltage_adjacencies_average_2.mat"), spmatrix=True)
+    for k in ("Austria", "Sweden", "England", "Mexico"):
+        A = sp.csr_matrix(v[k]).astype(np.float64)
+        A = (A + A.T) / 2 if (A != A.T).nnz else A
+        save("grid_%s" % k, A / A.max())
+
+
+if __name__ == "__main__":
+    main()
