@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the Krylov matrix-function hot path (BASELINE.json).
+
+Workload (config C3): synthetic power-law graph n = 1M, nnz = 20M (Chung-Lu,
+seed 20260310), A scaled by 1/lambda_max-estimate, 512 Rademacher probes PER GPU, m = 30 Lanczos
+steps per probe, trace(exp(A)) by stochastic Lanczos quadrature.  One "step" = one full pass
+(512 x 30 = 15 360 Krylov matvecs per GPU).  A is replicated, probes are sharded across ranks, one
+NCCL all-reduce of the partial trace per step (weak scaling: per-GPU work is fixed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric: Krylov matvecs/sec (an n x k SpMM counts k).  `value` = device-resident probes;
+`e2e` = through the public host-buffer call kr_slq_trace (pinned host probes -> device, result back).
+`--impl reference` times the reference's CPU algorithm (the NumPy/SciPy oracle: the reference is
+MATLAB-only and cannot run here) on the host cores with the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_NODES = int(os.environ.get("KR_BENCH_N", 1_000_000))
+NNZ = int(os.environ.get("KR_BENCH_NNZ", 20_000_000))
+K_PROBES = int(os.environ.get("KR_BENCH_K", 512))
+M_STEPS = int(os.environ.get("KR_BENCH_M", 30))
+GRAPH_SEED = 20260310
+PROBE_SEED = 1
+METRIC = "krylov_matvecs_per_sec"
+UNIT = "matvec/s"
+
+
+def build_graph():
+    from krylov_robustness_b200.graphs import power_law_graph, spectral_radius_estimate
+    A = power_law_graph(N_NODES, NNZ, 2.2, GRAPH_SEED)
+    lam = spectral_radius_estimate(A, 30)
+    A = A * (1.0 / lam)          # uniform value -> stored pattern-only on the device
+    return A.tocsr(), lam
+
+
+def config_dict(world):
+    return {"workload": "C3: power-law n=%d nnz=%d, %d Rademacher probes/GPU, Lanczos m=%d, trace(exp(A)) by SLQ"
+                        % (N_NODES, NNZ, K_PROBES, M_STEPS),
+            "n": N_NODES, "nnz": NNZ, "probes_per_gpu": K_PROBES, "lanczos_steps": M_STEPS,
+            "sharding": "A replicated, probes split across %d rank(s), 1 all-reduce/step" % world,
+            "cache": "inputs larger than L2 (each dense block is %.1f GB)" % (N_NODES * K_PROBES * 8 / 1e9)}
+
+
+# ------------------------------------------------------------------------------- CPU arms
+def _cpu_worker(args):
+    A, Z, m = args
+    import oracle
+    return oracle.slq_trace(A, Z, m, "exp")[0]
+
+
+def cpu_slq_rate(A, cols_per_proc, procs, m):
+    """matvecs/s of the oracle's SLQ on `procs` host processes (each: cols_per_proc probes)."""
+    from krylov_robustness_b200.engine import rademacher_host
+    import multiprocessing as mp
+    n = A.shape[0]
+    jobs = [(A, rademacher_host(n, cols_per_proc, PROBE_SEED, col_offset=p * cols_per_proc), m) for p in range(procs)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        _cpu_worker(jobs[0])
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_worker, jobs)
+    dt = time.perf_counter() - t0
+    return procs * cols_per_proc * m / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    A, _ = build_graph()
+    cores = os.cpu_count() or 1
+    cols = 2
+    times = []
+    for it in range(args.warmup + args.steps):
+        rate, dt = cpu_slq_rate(A, cols, cores, M_STEPS)
+        if it >= args.warmup:
+            times.append((rate, dt))
+    rate = float(np.mean([r for r, _ in times]))
+    ms = float(np.mean([d for _, d in times]) * 1e3)
+    sample = "%d probes (%d per process x %d processes) x %d Lanczos steps of the same graph per step" % (
+        cols * cores, cols, cores, M_STEPS)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(1),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference is MATLAB-only (no MATLAB/Octave in the image): this is the NumPy/SciPy "
+                    "oracle port of functions/*.m on the host cores"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import krylov_robustness_b200 as kr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    A, lam = build_graph()
+    n, nnz = A.shape[0], A.nnz
+    ctx = kr.Context(local)
+    M = kr.Matrix(A, ctx)
+    k, m = K_PROBES, M_STEPS
+    Zdev = kr.Dense(n, k, ctx).fill_rademacher(PROBE_SEED, col_offset=rank * k)
+    # pinned host copy of the same probes for the end-to-end arm (column-major n x k)
+    Zpin = torch.empty((k, n), dtype=torch.float64, pin_memory=True)
+    Zpin.numpy()[:] = Zdev.download().T
+    zptr = Zpin.data_ptr()
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def reduce_trace(tr_local):
+        # one collective per step: sum of the per-rank partial traces (tiny; latency-bound)
+        acc.fill_(tr_local / world)
+        if world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        return acc
+
+    def step_dev():
+        return reduce_trace(kr.slq_trace(M, Zdev, m, "exp"))
+
+    import ctypes as C
+    from krylov_robustness_b200._lib import check
+
+    def step_e2e():
+        tr = C.c_double()
+        check(ctx.lib.kr_slq_trace(ctx.h, M.h, k, C.c_void_p(zptr), n, m, 0, C.byref(tr), None, None, None))
+        return float(reduce_trace(tr.value).item())       # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), last
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    ctx.set_timing(True)
+    ctx.spmm_time(reset=True)
+    c0 = ctx.counters()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, tr_dev = timed(step_dev, args.steps)
+    clocks = sampler.stop() if sampler else None
+    c1 = ctx.counters()
+    spmm_ms, spmm_launches = ctx.spmm_time(reset=True)
+    ctx.set_timing(False)
+    tr_value = float(tr_dev.item())
+
+    for _ in range(1):
+        step_e2e()
+    h0 = ctx.counters()
+    ms_e2e, tr_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
+    h1 = ctx.counters()
+    e2e_steps = max(1, min(args.steps, 3))
+
+    if rank == 0:
+        mv_step = k * m * world
+        value = mv_step * args.steps / (ms_dev * 1e-3)
+        e2e = mv_step * e2e_steps / (ms_e2e * 1e-3)
+        peaks = {}
+        src = "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+            src = "measured"
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        b_spmm = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * k
+        per_launch_ms = spmm_ms / max(spmm_launches, 1)
+        achieved = b_spmm / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "spmm_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        # bounded CPU sample: the oracle on one core, 4 probes x m steps of the same graph
+        cpu_rate, cpu_dt = cpu_slq_rate(A, 4, 1, m)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(world),
+            "trace_estimate": tr_value, "lambda_scale": lam,
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": (h1["h2d_bytes"] - h0["h2d_bytes"]) // e2e_steps,
+                    "d2h_bytes_per_step": (h1["d2h_bytes"] - h0["d2h_bytes"]) // e2e_steps + 8,
+                    "ms_per_step": ms_e2e / e2e_steps, "trace_estimate": tr_e2e},
+            "gpu_launches": c1["launches"] - c0["launches"],
+            "roofline": {"bound": "hbm", "kernel": "spmm_kernel<EpiDot> (CSR x 512-wide fp64 block + fused alpha dot)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "%s copy bandwidth (MEASURED_PEAKS.json)" % src if src == "measured"
+                         else "fallback 6650 GB/s (B200_PROFILING.md)",
+                         "algorithmic_bytes_per_launch": b_spmm, "ms_per_launch": per_launch_ms,
+                         "launches_timed": spmm_launches,
+                         "share_of_step": spmm_ms / ms_dev, "traffic": traffic},
+            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "oracle.slq_trace (NumPy/SciPy port of the reference path) on 4 probes x %d steps "
+                                       "of the same graph, %.1f s" % (m, cpu_dt)},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

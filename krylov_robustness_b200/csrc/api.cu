@@ -1,0 +1,349 @@
+// api.cu - extern "C" entry points of libkrylov_b200.so (see include/krylov_b200.h).
+// Single translation unit: all kernels live in the .cuh files included below.
+#include <memory>
+#include "common.cuh"
+#include "csr.cuh"
+#include "spmm.cuh"
+#include "dense.cuh"
+#include "slq.cuh"
+#include "theta_table.h"
+#include "smalldense.cuh"
+#include "pairs.cuh"
+#include "expmv.cuh"
+#include "blockkrylov.cuh"
+
+using namespace kr;
+
+static void destroy_fun_update_result(kr_ctx* c);
+
+struct kr_dense {
+    kr_ctx* ctx;
+    PanelBuf buf;
+};
+
+extern "C" {
+
+const char* kr_last_error(void) { return tls_error().c_str(); }
+const char* kr_version(void) { return "krylov_b200 0.1 (sm_100a)"; }
+
+// ----------------------------------------------------------------------------- context
+int kr_ctx_create(int device, kr_ctx** out) {
+    return guarded([&] {
+        if (!out) fail(KR_ERR_ARG, "kr_ctx_create: null output");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            fail(KR_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        }
+        if (device < 0 || device >= count) fail(KR_ERR_ARG, "device %d out of range (0..%d)", device, count - 1);
+        KR_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        KR_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            fail(KR_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                 prop.major, prop.minor);
+        kr_ctx* c = new kr_ctx();
+        c->device = device;
+        c->num_sms = prop.multiProcessorCount;
+        c->l2_bytes = (size_t)prop.l2CacheSize;
+        KR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        KR_CUBLAS(cublasCreate(&c->cublas));
+        KR_CUBLAS(cublasSetStream(c->cublas, c->stream));
+        KR_CUBLAS(cublasSetPointerMode(c->cublas, CUBLAS_POINTER_MODE_HOST));
+        KR_CUSOLVER(cusolverDnCreate(&c->cusolver));
+        KR_CUSOLVER(cusolverDnSetStream(c->cusolver, c->stream));
+        *out = c;
+    });
+}
+
+void kr_ctx_destroy(kr_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    destroy_fun_update_result(c);
+    for (auto& ev : c->spmm_events) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    c->trim();
+    if (c->cusolver) cusolverDnDestroy(c->cusolver);
+    if (c->cublas) cublasDestroy(c->cublas);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int kr_ctx_sync(kr_ctx* c) {
+    return guarded([&] {
+        KR_CUDA(cudaSetDevice(c->device));
+        KR_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int kr_ctx_counters(kr_ctx* c, int64_t out[5]) {
+    return guarded([&] {
+        for (int i = 0; i < 5; ++i) out[i] = c->counters[i];
+    });
+}
+
+int kr_ctx_set_timing(kr_ctx* c, int on) {
+    return guarded([&] { c->timing = on != 0; });
+}
+
+int kr_ctx_spmm_time(kr_ctx* c, int reset, double* ms, int64_t* launches) {
+    return guarded([&] {
+        KR_CUDA(cudaStreamSynchronize(c->stream));
+        for (auto& ev : c->spmm_events) {
+            float t = 0.f;
+            KR_CUDA(cudaEventElapsedTime(&t, ev.first, ev.second));
+            c->spmm_ms += t;
+            c->spmm_timed += 1;
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+        c->spmm_events.clear();
+        if (ms) *ms = c->spmm_ms;
+        if (launches) *launches = c->spmm_timed;
+        if (reset) {
+            c->spmm_ms = 0.0;
+            c->spmm_timed = 0;
+        }
+    });
+}
+
+void* kr_ctx_stream(kr_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ----------------------------------------------------------------------------- matrix
+int kr_matrix_create(kr_ctx* ctx, int64_t n, int64_t nnz, const int64_t* row_ptr, const int64_t* col_idx,
+                     const double* val, kr_matrix** out) {
+    return guarded([&] {
+        if (!ctx || !out || !row_ptr || (nnz > 0 && (!col_idx || !val)))
+            fail(KR_ERR_ARG, "kr_matrix_create: null argument");
+        if (n < 0 || nnz < 0 || row_ptr[0] != 0 || row_ptr[n] != nnz)
+            fail(KR_ERR_ARG, "kr_matrix_create: inconsistent row_ptr (the matrix A should be square, CSR, 0-based)");
+        KR_CUDA(cudaSetDevice(ctx->device));
+        std::unique_ptr<kr_matrix> M(new kr_matrix());
+        M->ctx = ctx;
+        M->host.n = n;
+        M->host.row_ptr.assign(row_ptr, row_ptr + n + 1);
+        M->host.col.resize(nnz);
+        M->host.val.assign(val, val + nnz);
+        for (int64_t i = 0; i < n; ++i)
+            if (row_ptr[i + 1] < row_ptr[i]) fail(KR_ERR_ARG, "kr_matrix_create: row_ptr not monotone");
+        for (int64_t p = 0; p < nnz; ++p) {
+            if (col_idx[p] < 0 || col_idx[p] >= n)
+                fail(KR_ERR_ARG, "kr_matrix_create: column index out of range (The matrix A should be square)");
+            M->host.col[p] = (int32_t)col_idx[p];
+        }
+        analyse_and_upload(M.get());
+        *out = M.release();
+    });
+}
+
+void kr_matrix_destroy(kr_matrix* A) {
+    if (!A) return;
+    cudaSetDevice(A->ctx->device);
+    delete A;
+}
+
+int kr_matrix_info(const kr_matrix* A, int64_t* n, int64_t* nnz, int* symmetric, int* pattern_only,
+                   int* nonnegative) {
+    return guarded([&] {
+        if (!A) fail(KR_ERR_ARG, "null matrix");
+        if (n) *n = A->dev.n;
+        if (nnz) *nnz = A->dev.nnz;
+        if (symmetric) *symmetric = A->symmetric;
+        if (pattern_only) *pattern_only = A->dev.pattern_only;
+        if (nonnegative) *nonnegative = A->nonnegative;
+    });
+}
+
+int kr_matrix_set_edges(kr_matrix* A, int64_t count, const int64_t* ii, const int64_t* jj, const double* v) {
+    return guarded([&] {
+        if (!A) fail(KR_ERR_ARG, "null matrix");
+        KR_CUDA(cudaSetDevice(A->ctx->device));
+        CsrHost& H = A->host;
+        const int64_t n = H.n;
+        // gather edits per row (both triangles), then rebuild the touched rows
+        std::map<int64_t, std::map<int32_t, double>> edits;
+        for (int64_t e = 0; e < count; ++e) {
+            int64_t i = ii[e] - 1, j = jj[e] - 1;
+            if (i < 0 || i >= n || j < 0 || j >= n) fail(KR_ERR_ARG, "kr_matrix_set_edges: index out of range");
+            edits[i][(int32_t)j] = v[e];
+            edits[j][(int32_t)i] = v[e];
+        }
+        CsrHost N;
+        N.n = n;
+        N.row_ptr.assign(n + 1, 0);
+        N.col.reserve(H.col.size() + 2 * count);
+        N.val.reserve(H.val.size() + 2 * count);
+        for (int64_t i = 0; i < n; ++i) {
+            auto it = edits.find(i);
+            if (it == edits.end()) {
+                N.col.insert(N.col.end(), H.col.begin() + H.row_ptr[i], H.col.begin() + H.row_ptr[i + 1]);
+                N.val.insert(N.val.end(), H.val.begin() + H.row_ptr[i], H.val.begin() + H.row_ptr[i + 1]);
+            } else {
+                std::map<int32_t, double> row;
+                for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) row[H.col[p]] = H.val[p];
+                for (auto& kv : it->second) row[kv.first] = kv.second;
+                for (auto& kv : row)
+                    if (kv.second != 0.0) {           // MATLAB sparse assignment of 0 removes the entry
+                        N.col.push_back(kv.first);
+                        N.val.push_back(kv.second);
+                    }
+            }
+            N.row_ptr[i + 1] = (int64_t)N.col.size();
+        }
+        H = std::move(N);
+        analyse_and_upload(A);
+    });
+}
+
+// ----------------------------------------------------------------------------- dense blocks
+int kr_dense_create(kr_ctx* ctx, int64_t n, int64_t k, kr_dense** out) {
+    return guarded([&] {
+        if (!ctx || !out || n < 0 || k < 0 || k > (1 << 20)) fail(KR_ERR_ARG, "kr_dense_create: bad argument");
+        KR_CUDA(cudaSetDevice(ctx->device));
+        std::unique_ptr<kr_dense> d(new kr_dense());
+        d->ctx = ctx;
+        d->buf.reset(ctx, n, (int)k);
+        *out = d.release();
+    });
+}
+
+void kr_dense_destroy(kr_dense* d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    delete d;
+}
+
+static void upload_cm(kr_ctx* ctx, const double* host, int64_t ld, PanelBuf& dst) {
+    const int64_t n = dst.n;
+    const int k = dst.cols;
+    if (ld < n) fail(KR_ERR_ARG, "leading dimension smaller than the number of rows");
+    DevBuf<double> stage(ctx, (size_t)std::max<int64_t>(n * k, 1));
+    if (n > 0 && k > 0) {
+        KR_CUDA(cudaMemcpy2DAsync(stage.p, n * sizeof(double), host, ld * sizeof(double), n * sizeof(double), k,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        ctx->counters[3] += n * k * (int64_t)sizeof(double);
+    }
+    cm_to_panel(ctx, stage.p, n, dst);
+    KR_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller's host buffer may go away
+}
+
+static void download_cm(kr_ctx* ctx, const PanelBuf& src, double* host, int64_t ld) {
+    const int64_t n = src.n;
+    const int k = src.cols;
+    if (ld < n) fail(KR_ERR_ARG, "leading dimension smaller than the number of rows");
+    DevBuf<double> stage(ctx, (size_t)std::max<int64_t>(n * k, 1));
+    panel_to_cm(ctx, src, stage.p, n);
+    if (n > 0 && k > 0) {
+        KR_CUDA(cudaMemcpy2DAsync(host, ld * sizeof(double), stage.p, n * sizeof(double), n * sizeof(double), k,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->counters[4] += n * k * (int64_t)sizeof(double);
+    }
+    KR_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+int kr_dense_upload(kr_dense* d, const double* host, int64_t ld) {
+    return guarded([&] {
+        if (!d || !host) fail(KR_ERR_ARG, "kr_dense_upload: null argument");
+        KR_CUDA(cudaSetDevice(d->ctx->device));
+        upload_cm(d->ctx, host, ld, d->buf);
+    });
+}
+
+int kr_dense_download(const kr_dense* d, double* host, int64_t ld) {
+    return guarded([&] {
+        if (!d || !host) fail(KR_ERR_ARG, "kr_dense_download: null argument");
+        KR_CUDA(cudaSetDevice(d->ctx->device));
+        download_cm(d->ctx, d->buf, host, ld);
+    });
+}
+
+int kr_dense_fill_rademacher(kr_dense* d, uint64_t seed, int64_t col_offset) {
+    return guarded([&] {
+        if (!d) fail(KR_ERR_ARG, "null block");
+        KR_CUDA(cudaSetDevice(d->ctx->device));
+        if (d->buf.elems() == 0) return;
+        KR_LAUNCH(d->ctx, rademacher_kernel, d->ctx->num_sms * 8, 256, 0, d->buf.p(), d->buf.n, d->buf.cols,
+                  d->buf.panels, seed, col_offset);
+    });
+}
+
+// ----------------------------------------------------------------------------- SpMM
+int kr_spmm_dev(kr_ctx* ctx, const kr_matrix* A, const kr_dense* X, kr_dense* Y) {
+    return guarded([&] {
+        if (!ctx || !A || !X || !Y) fail(KR_ERR_ARG, "kr_spmm_dev: null argument");
+        if (X->buf.n != A->dev.n) fail(KR_ERR_ARG, "The block vector b has wrong number of rows");
+        if (Y->buf.n != X->buf.n || Y->buf.cols != X->buf.cols || Y->buf.p() == X->buf.p())
+            fail(KR_ERR_ARG, "kr_spmm_dev: Y must be a distinct block of the same shape as X");
+        KR_CUDA(cudaSetDevice(ctx->device));
+        EpiPlain epi{Y->buf.p(), X->buf.p(), 1.0, 0.0};
+        launch_spmm(ctx, A->dev, X->buf.p(), X->buf.panels, epi, nullptr, X->buf.cols);
+    });
+}
+
+int kr_spmm(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* X, int64_t ldx, double* Y, int64_t ldy) {
+    return guarded([&] {
+        if (!ctx || !A || !X || !Y) fail(KR_ERR_ARG, "kr_spmm: null argument");
+        KR_CUDA(cudaSetDevice(ctx->device));
+        const int64_t n = A->dev.n;
+        PanelBuf xb(ctx, n, (int)k), yb(ctx, n, (int)k);
+        upload_cm(ctx, X, ldx, xb);
+        EpiPlain epi{yb.p(), xb.p(), 1.0, 0.0};
+        launch_spmm(ctx, A->dev, xb.p(), xb.panels, epi, nullptr, (int)k);
+        download_cm(ctx, yb, Y, ldy);
+    });
+}
+
+// ----------------------------------------------------------------------------- SLQ trace
+static void slq_finish(const SlqResult& R, int64_t m, double* tr, double* vals, double* alpha, double* beta) {
+    if (tr) *tr = R.tr;
+    const size_t k = R.vals.size();
+    if (vals) std::memcpy(vals, R.vals.data(), k * sizeof(double));
+    if (alpha || beta)
+        for (int64_t j = 0; j < m; ++j)
+            for (size_t c = 0; c < k; ++c) {       // output is m x k column-major
+                if (alpha) alpha[c * m + j] = R.alpha[(size_t)j * k + c];
+                if (beta) beta[c * m + j] = R.beta[(size_t)j * k + c];
+            }
+}
+
+int kr_slq_trace_dev(kr_ctx* ctx, const kr_matrix* A, const kr_dense* Z, int64_t m, int fun, double* tr,
+                     double* vals, double* alpha, double* beta) {
+    return guarded([&] {
+        if (!ctx || !A || !Z) fail(KR_ERR_ARG, "kr_slq_trace_dev: null argument");
+        if (fun < 0 || fun > 2) fail(KR_ERR_ARG, "unsupported function selector");
+        KR_CUDA(cudaSetDevice(ctx->device));
+        // work on a copy: the caller's probe block stays intact for the next step
+        PanelBuf W(ctx, Z->buf.n, Z->buf.cols);
+        KR_CUDA(cudaMemcpyAsync(W.p(), Z->buf.p(), (size_t)W.elems() * sizeof(double), cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+        SlqResult R = slq_run(ctx, A, W, (int)m, fun, alpha || beta);
+        slq_finish(R, m, tr, vals, alpha, beta);
+    });
+}
+
+int kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, int64_t ldz, int64_t m, int fun,
+                 double* tr, double* vals, double* alpha, double* beta) {
+    return guarded([&] {
+        if (!ctx || !A || !Z) fail(KR_ERR_ARG, "kr_slq_trace: null argument");
+        if (fun < 0 || fun > 2) fail(KR_ERR_ARG, "unsupported function selector");
+        KR_CUDA(cudaSetDevice(ctx->device));
+        PanelBuf W(ctx, A->dev.n, (int)k);
+        upload_cm(ctx, Z, ldz, W);
+        SlqResult R = slq_run(ctx, A, W, (int)m, fun, alpha || beta);
+        slq_finish(R, m, tr, vals, alpha, beta);
+    });
+}
+
+int kr_theta(double theta[100]) {
+    return guarded([&] { std::memcpy(theta, KR_THETA, sizeof(KR_THETA)); });
+}
+
+}  // extern "C"
+
+#include "api_l2.inc"
+

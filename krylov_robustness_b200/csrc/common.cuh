@@ -1,0 +1,229 @@
+// common.cuh - context, error handling, device-memory pool, launch accounting.
+// Part of libkrylov_b200 (sm_100a only).  No CPU fallback anywhere: every failure surfaces as a
+// negative kr_status with a thread-local message.
+#pragma once
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/krylov_b200.h"
+
+namespace kr {
+
+// ---------------------------------------------------------------------------------- errors
+inline std::string& tls_error() {
+    static thread_local std::string e;
+    return e;
+}
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error(code, buf);
+}
+
+#define KR_CUDA(call)                                                                           \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            ::kr::fail(KR_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, \
+                       __LINE__, cudaGetErrorString(e_));                                       \
+    } while (0)
+#define KR_CUBLAS(call)                                                                         \
+    do {                                                                                        \
+        cublasStatus_t s_ = (call);                                                             \
+        if (s_ != CUBLAS_STATUS_SUCCESS)                                                        \
+            ::kr::fail(KR_ERR_CUDA, "cuBLAS error %d at %s:%d", (int)s_, __FILE__, __LINE__);   \
+    } while (0)
+#define KR_CUSOLVER(call)                                                                       \
+    do {                                                                                        \
+        cusolverStatus_t s_ = (call);                                                           \
+        if (s_ != CUSOLVER_STATUS_SUCCESS)                                                      \
+            ::kr::fail(KR_ERR_CUDA, "cuSOLVER error %d at %s:%d", (int)s_, __FILE__, __LINE__); \
+    } while (0)
+
+// wraps an extern "C" body: exceptions -> status + message
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return KR_OK;
+    } catch (const Error& e) {
+        tls_error() = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        tls_error() = "host allocation failed";
+        return KR_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        tls_error() = e.what();
+        return KR_ERR_ARG;
+    }
+}
+
+}  // namespace kr
+
+// ---------------------------------------------------------------------------------- context
+struct kr_ctx {
+    int device = 0;
+    int num_sms = 148;
+    size_t l2_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cublasHandle_t cublas = nullptr;
+    cusolverDnHandle_t cusolver = nullptr;
+    // counters: launches, spmm launches, matvecs, h2d bytes, d2h bytes
+    int64_t counters[5] = {0, 0, 0, 0, 0};
+    // optional SpMM timing
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spmm_events;
+    double spmm_ms = 0.0;
+    int64_t spmm_timed = 0;
+    // size-bucketed free lists (bytes rounded up to a power of two >= 512)
+    std::multimap<size_t, void*> pool;
+    size_t pool_bytes = 0;
+    // result of the last kr_fun_update, kept on the device until fetched
+    struct FunUpdateResult* last_fun_update = nullptr;
+
+    void* alloc(size_t bytes);
+    void release(void* p, size_t bytes);
+    void trim();
+};
+
+namespace kr {
+
+inline size_t bucket(size_t bytes) {
+    size_t b = 512;
+    while (b < bytes) b <<= 1;
+    // beyond 64 MiB round to 16 MiB multiples instead of powers of two (180 GB is not infinite)
+    if (b > (size_t(64) << 20)) {
+        const size_t g = size_t(16) << 20;
+        b = (bytes + g - 1) / g * g;
+    }
+    return b;
+}
+
+// RAII device buffer drawing from the context pool.
+template <class T>
+struct DevBuf {
+    kr_ctx* ctx = nullptr;
+    T* p = nullptr;
+    size_t count = 0;
+    DevBuf() = default;
+    DevBuf(kr_ctx* c, size_t n) { reset(c, n); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : ctx(o.ctx), p(o.p), count(o.count) { o.p = nullptr; o.count = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            free();
+            ctx = o.ctx; p = o.p; count = o.count;
+            o.p = nullptr; o.count = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { free(); }
+    void reset(kr_ctx* c, size_t n) {
+        free();
+        ctx = c;
+        count = n;
+        p = n ? static_cast<T*>(c->alloc(n * sizeof(T))) : nullptr;
+    }
+    void free() {
+        if (p) ctx->release(p, count * sizeof(T));
+        p = nullptr;
+        count = 0;
+    }
+    size_t bytes() const { return count * sizeof(T); }
+    void zero() { if (p) KR_CUDA(cudaMemsetAsync(p, 0, bytes(), ctx->stream)); }
+    void upload(const T* h, size_t n) {
+        KR_CUDA(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->counters[3] += (int64_t)(n * sizeof(T));
+    }
+    void download(T* h, size_t n) const {
+        KR_CUDA(cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        KR_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->counters[4] += (int64_t)(n * sizeof(T));
+    }
+    std::vector<T> to_host() const {
+        std::vector<T> h(count);
+        if (count) download(h.data(), count);
+        return h;
+    }
+};
+
+inline void check_launch(kr_ctx* ctx, const char* name) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(KR_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+    }
+    ctx->counters[0] += 1;
+}
+
+#define KR_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);        \
+        ::kr::check_launch((ctx), #kernel);                                     \
+    } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace kr
+
+inline void* kr_ctx::alloc(size_t bytes) {
+    size_t b = kr::bucket(bytes);
+    auto it = pool.find(b);
+    if (it != pool.end()) {
+        void* p = it->second;
+        pool.erase(it);
+        pool_bytes -= b;
+        return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, b);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        trim();
+        e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            kr::fail(KR_ERR_NOMEM, "device allocation of %zu bytes failed: %s", b, cudaGetErrorString(e));
+        }
+    }
+    return p;
+}
+
+inline void kr_ctx::release(void* p, size_t bytes) {
+    size_t b = kr::bucket(bytes);
+    // keep at most 48 GiB cached; large one-off buffers go straight back to the driver
+    if (pool_bytes + b > (size_t(48) << 30)) {
+        cudaStreamSynchronize(stream);
+        cudaFree(p);
+        return;
+    }
+    pool.emplace(b, p);
+    pool_bytes += b;
+}
+
+inline void kr_ctx::trim() {
+    cudaStreamSynchronize(stream);
+    for (auto& kv : pool) cudaFree(kv.second);
+    pool.clear();
+    pool_bytes = 0;
+}

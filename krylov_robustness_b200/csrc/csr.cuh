@@ -1,0 +1,208 @@
+// csr.cuh - device-resident CSR adjacency + host-side preprocessing (row binning / tiling).
+//
+// Replaces MATLAB's sparse A on the path `w = A*w` (functions/lanczos_krylov.m:81,
+// functions/arnoldi_krylov.m:86, functions/expmv.m:77, functions/normAm.m:20).
+//
+// Layout in HBM: row_ptr int32[n+1], col_idx int32[nnz], val fp64[nnz] (omitted when every stored
+// value is the same number -> 4 B per nonzero instead of 12).  Rows are NOT physically permuted;
+// instead `row_order` lists rows by decreasing length and `tiles` cuts that list into CTA work
+// items of roughly equal nonzero count whose rows all use the same lanes-per-row class, so a warp
+// never mixes a 4000-long hub row with length-3 rows.
+#pragma once
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace kr {
+
+struct RowTile {
+    int start;      // offset into row_order
+    int count;      // rows in this tile
+    int lanes_log2; // lanes per row: 2 (4 lanes) .. 5 (32 lanes)
+    int pad;
+};
+
+struct CsrHost {
+    int64_t n = 0;
+    std::vector<int64_t> row_ptr;
+    std::vector<int32_t> col;
+    std::vector<double> val;
+};
+
+struct CsrDevView {
+    int n;
+    int ntiles;
+    const int* __restrict__ row_ptr;
+    const int* __restrict__ col;
+    const double* __restrict__ val;   // nullptr => all values == uval
+    double uval;
+    const int* __restrict__ row_order;
+    const RowTile* __restrict__ tiles;
+};
+
+struct CsrDev {
+    int64_t n = 0, nnz = 0;
+    DevBuf<int> row_ptr, col, row_order;
+    DevBuf<double> val;
+    DevBuf<RowTile> tiles;
+    int ntiles = 0;
+    bool pattern_only = false;
+    double uval = 1.0;
+    CsrDevView view() const {
+        CsrDevView v;
+        v.n = (int)n;
+        v.ntiles = ntiles;
+        v.row_ptr = row_ptr.p;
+        v.col = col.p;
+        v.val = pattern_only ? nullptr : val.p;
+        v.uval = uval;
+        v.row_order = row_order.p;
+        v.tiles = tiles.p;
+        return v;
+    }
+};
+
+inline CsrHost transpose(const CsrHost& A) {
+    CsrHost T;
+    T.n = A.n;
+    const int64_t nnz = A.row_ptr[A.n];
+    T.row_ptr.assign(A.n + 1, 0);
+    T.col.resize(nnz);
+    T.val.resize(nnz);
+    for (int64_t p = 0; p < nnz; ++p) T.row_ptr[A.col[p] + 1]++;
+    for (int64_t i = 0; i < A.n; ++i) T.row_ptr[i + 1] += T.row_ptr[i];
+    std::vector<int64_t> next(T.row_ptr.begin(), T.row_ptr.end() - 1);
+    for (int64_t i = 0; i < A.n; ++i)
+        for (int64_t p = A.row_ptr[i]; p < A.row_ptr[i + 1]; ++p) {
+            int64_t q = next[A.col[p]]++;
+            T.col[q] = (int32_t)i;
+            T.val[q] = A.val[p];
+        }
+    return T;
+}
+
+// Rows must have sorted, duplicate-free columns for the symmetry comparison to be exact.
+inline void canonicalize(CsrHost& A) {
+    const int64_t n = A.n;
+    bool sorted = true;
+    for (int64_t i = 0; i < n && sorted; ++i)
+        for (int64_t p = A.row_ptr[i] + 1; p < A.row_ptr[i + 1]; ++p)
+            if (A.col[p - 1] >= A.col[p]) { sorted = false; break; }
+    if (sorted) return;
+    CsrHost T = transpose(A);      // two transposes = stable counting sort by column
+    A = transpose(T);
+    // merge duplicates (sum, as MATLAB's sparse() does)
+    std::vector<int64_t> rp(n + 1, 0);
+    int64_t w = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t begin = w;
+        for (int64_t p = A.row_ptr[i]; p < A.row_ptr[i + 1]; ++p) {
+            if (w > begin && A.col[w - 1] == A.col[p]) A.val[w - 1] += A.val[p];
+            else { A.col[w] = A.col[p]; A.val[w] = A.val[p]; ++w; }
+        }
+        rp[i + 1] = w;
+    }
+    A.row_ptr = rp;
+    A.col.resize(w);
+    A.val.resize(w);
+}
+
+inline void upload_csr(kr_ctx* ctx, const CsrHost& H, CsrDev& D) {
+    const int64_t n = H.n, nnz = H.row_ptr[n];
+    if (n >= (int64_t(1) << 31) - 64 || nnz >= (int64_t(1) << 31) - 64)
+        fail(KR_ERR_UNSUPPORTED, "matrix too large for 32-bit device indices (n=%lld nnz=%lld)",
+             (long long)n, (long long)nnz);
+    D.n = n;
+    D.nnz = nnz;
+    std::vector<int> rp(n + 1);
+    for (int64_t i = 0; i <= n; ++i) rp[i] = (int)H.row_ptr[i];
+    D.row_ptr.reset(ctx, n + 1);
+    D.row_ptr.upload(rp.data(), n + 1);
+    D.col.reset(ctx, std::max<int64_t>(nnz, 1));
+    if (nnz) D.col.upload(H.col.data(), nnz);
+    bool uniform = nnz > 0;
+    for (int64_t p = 1; p < nnz && uniform; ++p) uniform = (H.val[p] == H.val[0]);
+    D.pattern_only = uniform;
+    D.uval = uniform ? H.val[0] : 1.0;
+    if (!uniform) {
+        D.val.reset(ctx, std::max<int64_t>(nnz, 1));
+        if (nnz) D.val.upload(H.val.data(), nnz);
+    } else {
+        D.val.free();
+    }
+    // ---- row order: decreasing length (stable), then tiles of ~equal nonzero count per lane class
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return (rp[a + 1] - rp[a]) > (rp[b + 1] - rp[b]);
+    });
+    auto lane_class = [](int len) { return len >= 64 ? 5 : len >= 20 ? 4 : len >= 7 ? 3 : 2; };
+    std::vector<RowTile> tiles;
+    const int64_t target_nnz = 6144;
+    const int max_rows = 1024;
+    int64_t i = 0;
+    while (i < n) {
+        int cls = lane_class(rp[order[i] + 1] - rp[order[i]]);
+        int64_t acc = 0;
+        int64_t j = i;
+        while (j < n && j - i < max_rows) {
+            int len = rp[order[j] + 1] - rp[order[j]];
+            if (lane_class(len) != cls) break;
+            if (j > i && acc + len > target_nnz) break;
+            acc += len;
+            ++j;
+        }
+        tiles.push_back(RowTile{(int)i, (int)(j - i), cls, 0});
+        i = j;
+    }
+    D.ntiles = (int)tiles.size();
+    D.row_order.reset(ctx, std::max<int64_t>(n, 1));
+    if (n) D.row_order.upload(order.data(), n);
+    D.tiles.reset(ctx, std::max<size_t>(tiles.size(), 1));
+    if (!tiles.empty()) D.tiles.upload(tiles.data(), tiles.size());
+    KR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging vectors die here
+}
+
+}  // namespace kr
+
+struct kr_matrix {
+    kr_ctx* ctx = nullptr;
+    kr::CsrHost host;          // kept for kr_matrix_set_edges and host-side glue
+    kr::CsrDev dev;            // A
+    kr::CsrDev devT;           // A' (only when !symmetric)
+    bool symmetric = true;
+    bool nonnegative = true;
+    double trace = 0.0;
+    double norm1 = 0.0;        // max column abs sum
+    const kr::CsrDev& T() const { return symmetric ? dev : devT; }
+};
+
+namespace kr {
+
+inline void analyse_and_upload(kr_matrix* M) {
+    CsrHost& H = M->host;
+    canonicalize(H);
+    const int64_t n = H.n, nnz = H.row_ptr[n];
+    CsrHost T = transpose(H);
+    M->symmetric = (T.row_ptr == H.row_ptr) && (T.col == H.col) && (T.val == H.val);
+    M->nonnegative = true;
+    M->trace = 0.0;
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) {
+            if (H.val[p] < 0) M->nonnegative = false;
+            if (H.col[p] == i) M->trace += H.val[p];
+        }
+    M->norm1 = 0.0;   // max column abs-sum = max row abs-sum of A'
+    for (int64_t i = 0; i < n; ++i) {
+        double s = 0;
+        for (int64_t p = T.row_ptr[i]; p < T.row_ptr[i + 1]; ++p) s += std::abs(T.val[p]);
+        M->norm1 = std::max(M->norm1, s);
+    }
+    (void)nnz;
+    upload_csr(M->ctx, H, M->dev);
+    if (!M->symmetric) upload_csr(M->ctx, T, M->devT);
+    else { M->devT = CsrDev(); }
+}
+
+}  // namespace kr

@@ -1,0 +1,83 @@
+"""GPU parity: SpMM and the throughput-mode SLQ estimator against the oracle (through the C ABI)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kr():
+    import krylov_robustness_b200 as kr
+    return kr
+
+
+@pytest.mark.parametrize("gname", ["oregon_A0", "oregon_A8", "transport_Rome", "grid_England"])
+@pytest.mark.parametrize("k", [1, 2, 8, 10, 37])
+def test_spmm_matches_scipy(kr, graphs, gname, k):
+    A = graphs(gname)
+    n = A.shape[0]
+    X = np.random.default_rng(k).standard_normal((n, k))
+    M = kr.Matrix(A)
+    Y = M @ X
+    ref = A @ X
+    scale = (abs(A) @ np.abs(X)).max()
+    assert np.abs(Y - ref).max() <= 1e-14 * scale           # fp64, differs only by summation order
+    info = M.info()
+    assert info["symmetric"] and info["nnz"] == A.nnz
+    assert info["pattern_only"] == gname.startswith(("oregon", "transport"))
+
+
+def test_spmm_unsymmetric_ragged_and_empty_rows(kr):
+    rng = np.random.default_rng(0)
+    n = 3000
+    A = sp.random(n, n, density=0.002, random_state=1, format="lil")
+    A[5, :] = 0                       # empty row
+    A[7, :] = rng.standard_normal(n)  # one full row (n nonzeros)
+    A[:, 11] = 0                      # empty column
+    A = A.tocsr()
+    X = rng.standard_normal((n, 5))
+    M = kr.Matrix(A)
+    assert not M.info()["symmetric"]
+    Y = M @ X
+    ref = A @ X
+    assert np.abs(Y - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.all(Y[5] == 0)
+
+
+def test_spmm_errors(kr, graphs):
+    M = kr.Matrix(graphs("oregon_A0"))
+    with pytest.raises(ValueError, match="wrong number of rows"):
+        M @ np.ones((5, 2))
+    with pytest.raises(ValueError, match="should be square"):
+        kr.Matrix(sp.csr_matrix(np.ones((3, 4))))
+
+
+def test_dense_roundtrip_and_rademacher(kr):
+    X = np.random.default_rng(3).standard_normal((1000, 13))
+    D = kr.Dense(1000, 13).upload(X)
+    assert np.array_equal(D.download(), X)
+    R = kr.Dense(777, 9).fill_rademacher(42, col_offset=5).download()
+    assert np.array_equal(R, kr.rademacher_host(777, 9, 42, col_offset=5))
+    assert set(np.unique(R)) == {-1.0, 1.0}
+
+
+@pytest.mark.parametrize("gname,fun", [("oregon_A0", "exp"), ("transport_Rome", "exp"), ("grid_Mexico", "cosh"),
+                                       ("oregon_A8", "sinh")])
+def test_slq_matches_oracle(kr, graphs, gname, fun):
+    import oracle as O
+    A = graphs(gname)
+    if gname.startswith("oregon"):
+        A = A / 8.0                                         # keep exp in a comfortable range
+    n = A.shape[0]
+    Z = kr.rademacher_host(n, 24, 7)
+    tr, vals, al, be = kr.slq_trace(A, Z, 20, fun, return_details=True)
+    otr, ovals, oal, obe = O.slq_trace(A, Z, 20, fun)
+    # fp64 tolerance of the north star: 1e-10 relative on traces
+    assert abs(tr - otr) <= 1e-10 * abs(otr)
+    assert np.max(np.abs(vals - ovals)) <= 1e-10 * np.max(np.abs(ovals))
+    assert np.max(np.abs(al - oal)) <= 1e-9 * np.max(np.abs(oal))
+    # device-resident probes give the identical result (same kernels, same order)
+    D = kr.Dense(n, 24).upload(Z)
+    assert kr.slq_trace(kr.Matrix(A), D, 20, fun) == tr
+    assert kr.slq_trace(kr.Matrix(A), D, 20, fun) == tr      # bit-reproducible run to run
