@@ -11,6 +11,8 @@
 #include "pairs.cuh"
 #include "expmv.cuh"
 #include "blockkrylov.cuh"
+#include "entries.cuh"
+#include "mctrace.cuh"
 
 using namespace kr;
 

@@ -1,1 +1,381 @@
+// expmv.cuh - Al-Mohy & Higham's expmv on the device: normAm, select_taylor_degree, Taylor stages.
+// Reference: functions/expmv.m, functions/select_taylor_degree.m, functions/normAm.m.
+//
+// The Taylor inner loop (expmv.m:75-88) is ONE fused SpMM launch per term (b' = coef*(A-mu I)b,
+// f += b', per-row abs-sums of b' and f) plus one tiny reduction kernel that evaluates the
+// early-termination test c1 + c2 <= tol*||f||_inf ON THE DEVICE and raises a flag; later launches
+// of the stage see the flag and return immediately, so a whole expmv call is enqueued without a
+// single host round-trip.  The 1-norm power sequence of normAm (A >= 0: e <- A'e, exact) is computed
+// once for all p = 1..p_max (9 SpMVs instead of 44; the reported mv stays the reference's count).
 #pragma once
+#include <cmath>
+
+#include "dense.cuh"
+#include "theta_table.h"
+
+namespace kr {
+
+// ---------------------------------------------------------------------------------- norms
+// partial[b] = max over the CTA's rows of sum_panels ra[panel][r]
+__global__ void rowsum_max_partial_kernel(const double* __restrict__ ra, int64_t n, int panels,
+                                          double* __restrict__ partial, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double red[8];
+    double m = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < panels; ++q) s += ra[(int64_t)q * n + r];
+        m = fmax(m, s);
+    }
+    for (int off = 16; off; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        partial[blockIdx.x] = m;
+    }
+}
+
+// ra[panel][r] = sum of |X(r, c)| over the panel's 8 columns
+__global__ void rowabs_kernel(const double* __restrict__ X, int64_t n, int panels, double* __restrict__ ra) {
+    const int64_t total = n * panels;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const double* x = X + e * PW;
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < PW; ++c) s += fabs(x[c]);
+        ra[e] = s;
+    }
+}
+
+struct TaylorCtl {
+    double c1;        // running ||b||_inf of the previous term
+    double c2, nf;    // scratch
+    int done;         // early-termination flag of the current stage
+    int mv;           // products actually computed
+};
+
+// mode 0: c1 = max(partial_b)            (stage start, expmv.m:74)
+// mode 1: c2 = max(partial_b), nf = max(partial_f); mv++; test (expmv.m:78-86)
+__global__ void taylor_ctl_kernel(TaylorCtl* ctl, const double* __restrict__ pb, const double* __restrict__ pf,
+                                  int nparts, int mode, int full_term, double tol) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (mode == 0) {
+        double m = 0.0;
+        for (int i = 0; i < nparts; ++i) m = fmax(m, pb[i]);
+        ctl->c1 = m;
+        ctl->done = 0;
+        return;
+    }
+    if (ctl->done) return;
+    double c2 = 0.0, nf = 0.0;
+    for (int i = 0; i < nparts; ++i) {
+        c2 = fmax(c2, pb[i]);
+        nf = fmax(nf, pf[i]);
+    }
+    ctl->mv += 1;
+    ctl->c2 = c2;
+    ctl->nf = nf;
+    if (!full_term) {
+        if (ctl->c1 + c2 <= tol * nf) ctl->done = 1;
+        else ctl->c1 = c2;
+    }
+}
+
+// f = eta * f ; b = f        (expmv.m:91)
+__global__ void stage_end_kernel(double* __restrict__ F, double* __restrict__ B, int64_t total, double eta) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        double v = eta * F[e];
+        F[e] = v;
+        B[e] = v;
+    }
+}
+
+__global__ void fill_kernel(double* __restrict__ X, int64_t total, double v) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) X[e] = v;
+}
+
+// max |X(r, 0)| of a one-column panel block -> out[0] (single CTA; n is modest work: one pass)
+__global__ void col0_absmax_kernel(const double* __restrict__ X, int64_t n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double m = 0.0;
+    for (int64_t r = threadIdx.x; r < n; r += blockDim.x) m = fmax(m, fabs(X[r * PW]));
+    for (int off = 16; off; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        out[0] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------- shifted-matrix facts
+struct ShiftFacts {
+    double norm1;      // ||A - mu I||_1
+    bool nonneg;       // every entry of (A - mu I) >= 0
+};
+
+inline ShiftFacts shifted_facts(const kr_matrix* M, double mu) {
+    ShiftFacts f;
+    if (mu == 0.0) {
+        f.norm1 = M->norm1;
+        f.nonneg = M->nonnegative;
+        return f;
+    }
+    const CsrHost& H = M->host;
+    const int64_t n = H.n;
+    std::vector<double> colsum(n, 0.0);
+    f.nonneg = true;
+    for (int64_t i = 0; i < n; ++i) {
+        bool diag = false;
+        for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) {
+            double v = H.val[p];
+            if (H.col[p] == i) { v -= mu; diag = true; }
+            if (v < 0) f.nonneg = false;
+            colsum[H.col[p]] += std::abs(v);
+        }
+        if (!diag) {
+            colsum[i] += std::abs(mu);
+            if (-mu < 0) f.nonneg = false;
+        }
+    }
+    f.norm1 = 0.0;
+    for (int64_t i = 0; i < n; ++i) f.norm1 = std::max(f.norm1, colsum[i]);
+    return f;
+}
+
+// y = alpha * (Aop - mu I) x on one-column panel blocks
+inline void spmv_panel(kr_ctx* ctx, const CsrDev& Aop, const PanelBuf& x, PanelBuf& y, double alpha, double mu) {
+    EpiPlain epi{y.p(), x.p(), alpha, mu};
+    launch_spmm(ctx, Aop, x.p(), 1, epi, nullptr, 1);
+}
+
+// ||((scale*(A - mu I))')^j 1||_inf for j = 1..jmax, valid when scale*(A - mu I) >= 0 (normAm.m:17-23).
+inline std::vector<double> power_norms_nonneg(kr_ctx* ctx, const kr_matrix* M, double scale, double mu, int jmax) {
+    const int64_t n = M->dev.n;
+    PanelBuf e0(ctx, n, 1), e1(ctx, n, 1);
+    e0.buf.zero();
+    e1.buf.zero();
+    // ones in column 0 only
+    {
+        std::vector<double> ones((size_t)n * PW, 0.0);
+        for (int64_t i = 0; i < n; ++i) ones[i * PW] = 1.0;
+        e0.buf.upload(ones.data(), ones.size());
+        KR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    DevBuf<double> out(ctx, jmax);
+    PanelBuf* a = &e0;
+    PanelBuf* b = &e1;
+    for (int j = 0; j < jmax; ++j) {
+        spmv_panel(ctx, M->T(), *a, *b, scale, mu);
+        KR_LAUNCH(ctx, col0_absmax_kernel, 1, 1024, 0, b->p(), n, out.p + j);
+        std::swap(a, b);
+    }
+    return out.to_host();
+}
+
+struct OneNormEst { double est; int nprod; };
+
+// Hager/Higham estimator with one column on (scale*(A-mu I))^m  - MATLAB normest1(@afun_power, 1)
+// as called from normAm.m:25-26.  Vectors live on the device (column 0 of one-column panels); the
+// handful of scalars per iteration come back through cuBLAS reductions.
+inline OneNormEst onenormest_power(kr_ctx* ctx, const kr_matrix* M, double scale, double mu, int m) {
+    const int64_t n = M->dev.n;
+    PanelBuf x(ctx, n, 1), y(ctx, n, 1), z(ctx, n, 1), t(ctx, n, 1);
+    x.buf.zero(); y.buf.zero(); z.buf.zero(); t.buf.zero();
+    std::vector<double> hx((size_t)n * PW, 0.0);
+    for (int64_t i = 0; i < n; ++i) hx[i * PW] = 1.0 / (double)n;
+    x.buf.upload(hx.data(), hx.size());
+    KR_CUDA(cudaStreamSynchronize(ctx->stream));
+    auto power = [&](const CsrDev& Aop, PanelBuf& in, PanelBuf& outv) {
+        // outv = Aop^m in (in is clobbered only through t)
+        PanelBuf* a = &in;
+        PanelBuf* b = &t;
+        PanelBuf* fin = &outv;
+        for (int i = 0; i < m; ++i) {
+            PanelBuf* dst = (i == m - 1) ? fin : b;
+            spmv_panel(ctx, Aop, *a, *dst, scale, mu);
+            a = dst;
+            b = (dst == &t) ? &z : &t;
+            if (b == fin) b = &t;
+        }
+    };
+    int nprod = 0;
+    double est_old = 0.0;
+    std::vector<int> hist;
+    std::vector<double> hy((size_t)n * PW), hz((size_t)n * PW);
+    for (int itn = 1; itn <= 5; ++itn) {
+        power(M->dev, x, y);
+        nprod += 1;
+        y.buf.download(hy.data(), hy.size());
+        double est = 0.0;
+        for (int64_t i = 0; i < n; ++i) est += std::abs(hy[i * PW]);
+        if (itn > 1 && est <= est_old) break;
+        est_old = est;
+        for (int64_t i = 0; i < n; ++i) hy[i * PW] = hy[i * PW] < 0 ? -1.0 : 1.0;
+        y.buf.upload(hy.data(), hy.size());
+        PanelBuf s2(ctx, n, 1);
+        s2.buf.zero();
+        power(M->T(), y, s2);
+        nprod += 1;
+        s2.buf.download(hz.data(), hz.size());
+        int64_t jmax = 0;
+        double zmax = 0.0, zx = 0.0;
+        for (int64_t i = 0; i < n; ++i) {
+            double a = std::abs(hz[i * PW]);
+            if (a > zmax) { zmax = a; jmax = i; }
+            zx += hz[i * PW] * hx[i * PW];
+        }
+        bool seen = false;
+        for (int v : hist) seen = seen || (v == (int)jmax);
+        if (itn > 1 && (zmax <= zx || seen)) break;
+        hist.push_back((int)jmax);
+        std::fill(hx.begin(), hx.end(), 0.0);
+        hx[jmax * PW] = 1.0;
+        x.buf.upload(hx.data(), hx.size());
+        KR_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return OneNormEst{est_old, nprod};
+}
+
+struct NormAm { double c; int64_t mv; };
+
+// [c, mv] = normAm(scale*(A - mu I), m)
+inline NormAm normAm_dev(kr_ctx* ctx, const kr_matrix* M, double scale, double mu, int m) {
+    ShiftFacts sf = shifted_facts(M, mu);
+    if (sf.nonneg && scale >= 0.0) {
+        std::vector<double> pn = power_norms_nonneg(ctx, M, scale, mu, m);
+        return NormAm{pn[m - 1], m};
+    }
+    OneNormEst e = onenormest_power(ctx, M, scale, mu, m);
+    return NormAm{e.est, (int64_t)e.nprod * m};
+}
+
+struct TaylorDegree {
+    std::vector<double> Mtab;   // m_max x (p_max-1) column-major
+    std::vector<double> alpha;
+    int64_t mv = 0;
+    int unA = 0;
+};
+
+// select_taylor_degree on scale*(A - mu I)        (select_taylor_degree.m:15-68)
+inline TaylorDegree select_taylor_degree_dev(kr_ctx* ctx, const kr_matrix* M, double scale, double mu,
+                                             int64_t ncols, int m_max, int p_max, bool force_estm) {
+    if (p_max < 2 || m_max > 60 || m_max + 1 < p_max * (p_max - 1)) fail(KR_ERR_ARG, ">>> Invalid p_max or m_max.");
+    TaylorDegree R;
+    R.alpha.assign(p_max - 1, 0.0);
+    ShiftFacts sf = shifted_facts(M, mu);
+    const double normA = std::abs(scale) * sf.norm1;
+    if (!force_estm && normA <= 4.0 * KR_THETA[m_max - 1] * p_max * (p_max + 3) / ((double)m_max * (double)ncols)) {
+        R.unA = 1;
+        for (auto& a : R.alpha) a = normA;
+    } else {
+        R.unA = 0;
+        std::vector<double> eta(p_max);
+        if (sf.nonneg && scale >= 0.0) {
+            std::vector<double> pn = power_norms_nonneg(ctx, M, scale, mu, p_max + 1);
+            for (int p = 1; p <= p_max; ++p) {
+                eta[p - 1] = std::pow(pn[p], 1.0 / (p + 1));
+                R.mv += p + 1;                 // the reference restarts from ones for every p (normAm.m:18-21)
+            }
+        } else {
+            for (int p = 1; p <= p_max; ++p) {
+                OneNormEst e = onenormest_power(ctx, M, scale, mu, p + 1);
+                eta[p - 1] = std::pow(e.est, 1.0 / (p + 1));
+                R.mv += (int64_t)e.nprod * (p + 1);
+            }
+        }
+        for (int p = 1; p < p_max; ++p) R.alpha[p - 1] = std::max(eta[p - 1], eta[p]);
+    }
+    R.Mtab.assign((size_t)m_max * (p_max - 1), 0.0);
+    for (int p = 2; p <= p_max; ++p)
+        for (int m = p * (p - 1) - 1; m <= m_max; ++m)
+            R.Mtab[(size_t)(p - 2) * m_max + (m - 1)] = R.alpha[p - 2] / KR_THETA[m - 1];
+    return R;
+}
+
+// (m, s) from the cost matrix     (expmv.m:57-67)
+inline void degree_from_M(const double* Mtab, int m_max, int pcols, double tt, int64_t* m_out, int64_t* s_out) {
+    double best = INFINITY;
+    int bestm = 1;
+    for (int m = 1; m <= m_max; ++m) {
+        double colmin = INFINITY;
+        for (int p = 0; p < pcols; ++p) {
+            double c = std::ceil(std::abs(tt) * Mtab[(size_t)p * m_max + (m - 1)]) * m;
+            if (c == 0.0) c = INFINITY;
+            colmin = std::min(colmin, c);
+        }
+        if (colmin < best) { best = colmin; bestm = m; }
+    }
+    double cost = std::isinf(best) ? 0.0 : best;
+    double s = std::max(cost / bestm, 1.0);
+    *m_out = bestm;
+    *s_out = (int64_t)s;
+}
+
+struct ExpmvInfo { int64_t s = 1, m = 0, mv = 0, mvd = 0; int unA = 0; };
+
+// F = exp(t A) B for panel-major device blocks.  B is clobbered.  Mtab may be null.
+inline ExpmvInfo expmv_dev(kr_ctx* ctx, const kr_matrix* M, double t, PanelBuf& B, PanelBuf& F,
+                           const double* Mtab, int m_max, int pcols, bool shift, bool full_term) {
+    const int64_t n = M->dev.n;
+    const int panels = B.panels;
+    ExpmvInfo info;
+    double mu = 0.0;
+    if (shift) mu = M->trace / (double)n;
+    double tt;
+    TaylorDegree td;
+    if (!Mtab) {
+        tt = 1.0;
+        td = select_taylor_degree_dev(ctx, M, t, mu, B.cols, 55, 8, false);
+        Mtab = td.Mtab.data();
+        m_max = 55;
+        pcols = 7;
+        info.mvd = td.mv;
+        info.mv = td.mv;
+        info.unA = td.unA;
+    } else {
+        tt = t;
+    }
+    const double tol = std::ldexp(1.0, -53);
+    if (t == 0.0) { info.m = 0; info.s = 1; }
+    else degree_from_M(Mtab, m_max, pcols, tt, &info.m, &info.s);
+    const double eta = shift ? std::exp(t * mu / (double)info.s) : 1.0;
+    const int64_t total = B.elems();
+    KR_CUDA(cudaMemcpyAsync(F.p(), B.p(), (size_t)total * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    PanelBuf Bn(ctx, n, B.cols);
+    DevBuf<double> rab(ctx, (size_t)n * panels), raf(ctx, (size_t)n * panels);
+    const int nparts = std::min<int64_t>(ctx->num_sms * 4, std::max<int64_t>(1, ceil_div(n, 256)));
+    DevBuf<double> pb(ctx, nparts), pf(ctx, nparts);
+    DevBuf<TaylorCtl> ctl(ctx, 1);
+    ctl.zero();
+    const int egrid = (int)std::min<int64_t>(ctx->num_sms * 8, std::max<int64_t>(1, ceil_div(total, 256)));
+    double* b = B.p();
+    double* bn = Bn.p();
+    for (int64_t i = 0; i < info.s; ++i) {
+        KR_LAUNCH(ctx, rowabs_kernel, egrid, 256, 0, b, n, panels, rab.p);
+        KR_LAUNCH(ctx, rowsum_max_partial_kernel, nparts, 256, 0, rab.p, n, panels, pb.p, (const int*)nullptr);
+        KR_LAUNCH(ctx, taylor_ctl_kernel, 1, 32, 0, ctl.p, pb.p, pf.p, nparts, 0, (int)full_term, tol);
+        const int* done = &ctl.p->done;
+        for (int64_t k = 1; k <= info.m; ++k) {
+            EpiTaylor epi;
+            epi.Bn = bn; epi.Bo = b; epi.F = F.p(); epi.rab = rab.p; epi.raf = raf.p;
+            epi.coef = t / ((double)info.s * (double)k);
+            epi.mu = mu;
+            launch_spmm(ctx, M->dev, b, panels, epi, done, 0);
+            KR_LAUNCH(ctx, rowsum_max_partial_kernel, nparts, 256, 0, rab.p, n, panels, pb.p, done);
+            KR_LAUNCH(ctx, rowsum_max_partial_kernel, nparts, 256, 0, raf.p, n, panels, pf.p, done);
+            KR_LAUNCH(ctx, taylor_ctl_kernel, 1, 32, 0, ctl.p, pb.p, pf.p, nparts, 1, (int)full_term, tol);
+            std::swap(b, bn);
+        }
+        KR_LAUNCH(ctx, stage_end_kernel, egrid, 256, 0, F.p(), b, total, eta);
+    }
+    TaylorCtl h;
+    KR_CUDA(cudaMemcpyAsync(&h, ctl.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    KR_CUDA(cudaStreamSynchronize(ctx->stream));
+    info.mv += h.mv;
+    ctx->counters[2] += (int64_t)h.mv * B.cols;
+    return info;
+}
+
+}  // namespace kr
