@@ -3,11 +3,14 @@
 // Replaces MATLAB's sparse A on the path `w = A*w` (functions/lanczos_krylov.m:81,
 // functions/arnoldi_krylov.m:86, functions/expmv.m:77, functions/normAm.m:20).
 //
-// Layout in HBM: row_ptr int32[n+1], col_idx int32[nnz], val fp64[nnz] (omitted when every stored
-// value is the same number -> 4 B per nonzero instead of 12).  Rows are NOT physically permuted;
-// instead `row_order` lists rows by decreasing length and `tiles` cuts that list into CTA work
-// items of roughly equal nonzero count whose rows all use the same lanes-per-row class, so a warp
-// never mixes a 4000-long hub row with length-3 rows.
+// Layout in HBM: the ROWS are stored sorted by decreasing length (`row_order[s]` = original index of
+// stored row s): row_ptr int32[n+1] over the stored order, col_idx int32[nnz] (ORIGINAL column
+// numbers - X and Y keep the caller's row numbering), val fp64[nnz] (omitted when every stored value
+// is the same number -> 4 B per nonzero instead of 12).  `tiles` cuts the stored order into CTA work
+// items: a tile is a run of rows of one lanes-per-row class whose nonzeros are CONTIGUOUS and fit the
+// CTA's shared-memory staging buffer (SPMM_CAP), so the kernel streams a tile's indices with coalesced
+// loads once and only the X gathers remain as dependent global loads.  Rows longer than
+// SPMM_LONG_ROW get a tile (and a whole CTA) of their own.
 #pragma once
 #include <algorithm>
 #include <numeric>
@@ -33,13 +36,17 @@ struct CsrHost {
 struct CsrDevView {
     int n;
     int ntiles;
-    const int* __restrict__ row_ptr;
+    const int* __restrict__ row_ptr;  // over the stored (sorted) row order
     const int* __restrict__ col;
     const double* __restrict__ val;   // nullptr => all values == uval
     double uval;
     const int* __restrict__ row_order;
     const RowTile* __restrict__ tiles;
 };
+
+constexpr int SPMM_CAP = 4096;        // nonzeros staged in shared memory per multi-row tile
+constexpr int SPMM_MAX_ROWS = 1024;   // rows per tile
+constexpr int SPMM_LONG_ROW = 1024;   // rows at least this long are processed by a whole CTA
 
 struct CsrDev {
     int64_t n = 0, nnz = 0;
@@ -117,41 +124,53 @@ inline void upload_csr(kr_ctx* ctx, const CsrHost& H, CsrDev& D) {
     D.nnz = nnz;
     std::vector<int> rp(n + 1);
     for (int64_t i = 0; i <= n; ++i) rp[i] = (int)H.row_ptr[i];
-    D.row_ptr.reset(ctx, n + 1);
-    D.row_ptr.upload(rp.data(), n + 1);
-    D.col.reset(ctx, std::max<int64_t>(nnz, 1));
-    if (nnz) D.col.upload(H.col.data(), nnz);
     bool uniform = nnz > 0;
     for (int64_t p = 1; p < nnz && uniform; ++p) uniform = (H.val[p] == H.val[0]);
     D.pattern_only = uniform;
     D.uval = uniform ? H.val[0] : 1.0;
-    if (!uniform) {
-        D.val.reset(ctx, std::max<int64_t>(nnz, 1));
-        if (nnz) D.val.upload(H.val.data(), nnz);
-    } else {
-        D.val.free();
-    }
-    // ---- row order: decreasing length (stable), then tiles of ~equal nonzero count per lane class
+    // ---- stored order: decreasing length (stable)
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         return (rp[a + 1] - rp[a]) > (rp[b + 1] - rp[b]);
     });
-    auto lane_class = [](int len) { return len >= 64 ? 5 : len >= 20 ? 4 : len >= 7 ? 3 : 2; };
+    std::vector<int> srp(n + 1, 0);
+    std::vector<int32_t> scol((size_t)std::max<int64_t>(nnz, 1));
+    std::vector<double> sval(uniform ? 1 : (size_t)std::max<int64_t>(nnz, 1));
+    for (int64_t s = 0; s < n; ++s) {
+        const int r = order[s];
+        const int len = rp[r + 1] - rp[r];
+        srp[s + 1] = srp[s] + len;
+        std::copy(H.col.begin() + rp[r], H.col.begin() + rp[r + 1], scol.begin() + srp[s]);
+        if (!uniform) std::copy(H.val.begin() + rp[r], H.val.begin() + rp[r + 1], sval.begin() + srp[s]);
+    }
+    D.row_ptr.reset(ctx, n + 1);
+    D.row_ptr.upload(srp.data(), n + 1);
+    D.col.reset(ctx, std::max<int64_t>(nnz, 1));
+    if (nnz) D.col.upload(scol.data(), nnz);
+    if (!uniform) {
+        D.val.reset(ctx, std::max<int64_t>(nnz, 1));
+        if (nnz) D.val.upload(sval.data(), nnz);
+    } else {
+        D.val.free();
+    }
+    // ---- tiles: runs of one lane class, nonzeros <= SPMM_CAP, rows <= SPMM_MAX_ROWS; long rows alone
+    auto lane_class = [](int len) {
+        return len >= SPMM_LONG_ROW ? 6 : len >= 64 ? 5 : len >= 20 ? 4 : len >= 7 ? 3 : 2;
+    };
     std::vector<RowTile> tiles;
-    const int64_t target_nnz = 6144;
-    const int max_rows = 1024;
     int64_t i = 0;
     while (i < n) {
-        int cls = lane_class(rp[order[i] + 1] - rp[order[i]]);
-        int64_t acc = 0;
-        int64_t j = i;
-        while (j < n && j - i < max_rows) {
-            int len = rp[order[j] + 1] - rp[order[j]];
-            if (lane_class(len) != cls) break;
-            if (j > i && acc + len > target_nnz) break;
-            acc += len;
-            ++j;
+        const int cls = lane_class(srp[i + 1] - srp[i]);
+        int64_t j = i + 1;
+        if (cls != 6) {
+            int64_t acc = srp[i + 1] - srp[i];
+            while (j < n && j - i < SPMM_MAX_ROWS) {
+                const int len = srp[j + 1] - srp[j];
+                if (lane_class(len) != cls || acc + len > SPMM_CAP) break;
+                acc += len;
+                ++j;
+            }
         }
         tiles.push_back(RowTile{(int)i, (int)(j - i), cls, 0});
         i = j;

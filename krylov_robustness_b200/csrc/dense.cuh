@@ -171,14 +171,29 @@ combine3_norm_kernel(const double* __restrict__ Y, const double* __restrict__ U1
     }
 }
 
-// out[col] = sum_b partial[b][col]   (fixed order)
-__global__ void sum_partials_kernel(const double* __restrict__ partial, int nblocks, int total_cols,
-                                    double* __restrict__ out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total_cols) return;
+// out[col] = sum_b partial[b][col] in a fixed order: 32 columns x 8 row-groups per CTA, every thread
+// sums a strided slice, the 8 slices meet in shared memory in index order (deterministic).
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const double* __restrict__ partial, int nblocks, int total_cols,
+                    double* __restrict__ out) {
+    __shared__ double sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * total_cols + c];
-    out[c] = s;
+    if (c < total_cols)
+        for (int b = ty; b < nblocks; b += 8) s += partial[(int64_t)b * total_cols + c];
+    sm[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < total_cols) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][tx];
+        out[c] = t;
+    }
+}
+
+inline void sum_partials(kr_ctx* ctx, const double* partial, int nblocks, int total_cols, double* out) {
+    KR_LAUNCH(ctx, sum_partials_kernel, (int)ceil_div(total_cols, 32), 256, 0, partial, nblocks, total_cols, out);
 }
 
 // ------------------------------------------------------------------ SLQ scalar recurrences
@@ -193,12 +208,10 @@ struct SlqState {
 };
 
 // after the SpMM of step j: alpha_j = s1^2 * (U1 . A U1); coefficients of the three-term update
-__global__ void slq_alpha_kernel(const double* __restrict__ partial, int nblocks, int total_cols,
-                                 SlqState st, int j) {
+__global__ void slq_alpha_kernel(const double* __restrict__ sums, int total_cols, SlqState st, int j) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= total_cols) return;
-    double d = 0.0;
-    for (int b = 0; b < nblocks; ++b) d += partial[(int64_t)b * total_cols + c];
+    const double d = sums[c];
     const double s1 = st.s1[c];
     const double a = s1 * s1 * d;
     st.alpha[(int64_t)j * total_cols + c] = a;
@@ -208,12 +221,10 @@ __global__ void slq_alpha_kernel(const double* __restrict__ partial, int nblocks
 }
 
 // after the update of step j: beta_j = ||w||; rotate scales
-__global__ void slq_beta_kernel(const double* __restrict__ partial, int nblocks, int total_cols,
-                                SlqState st, int j) {
+__global__ void slq_beta_kernel(const double* __restrict__ sums, int total_cols, SlqState st, int j) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= total_cols) return;
-    double d = 0.0;
-    for (int b = 0; b < nblocks; ++b) d += partial[(int64_t)b * total_cols + c];
+    const double d = sums[c];
     const double b = sqrt(d);
     st.beta[(int64_t)j * total_cols + c] = b;
     st.s0[c] = st.s1[c];
@@ -221,12 +232,11 @@ __global__ void slq_beta_kernel(const double* __restrict__ partial, int nblocks,
     st.beta_prev[c] = b;
 }
 
-__global__ void slq_init_kernel(const double* __restrict__ partial, int nblocks, int total_cols,
-                                SlqState st, double* __restrict__ nrm2) {
+__global__ void slq_init_kernel(const double* __restrict__ sums, int total_cols, SlqState st,
+                                double* __restrict__ nrm2) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= total_cols) return;
-    double d = 0.0;
-    for (int b = 0; b < nblocks; ++b) d += partial[(int64_t)b * total_cols + c];
+    const double d = sums[c];
     nrm2[c] = d;
     st.s1[c] = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
     st.s0[c] = 0.0;

@@ -250,7 +250,7 @@ inline EntriesResult entries_run(kr_ctx* ctx, const kr_matrix* M, const std::vec
                 PtrChunk pc;
                 for (int l = 0; l < MD_CHUNK; ++l) pc.v[l] = l < nl ? V[l0 + l]->p() : nullptr;
                 KR_LAUNCH(ctx, multi_dot_kernel, cgrid, COL_THREADS, 0, pc, nl, W.p(), n, tc, partial.p);
-                KR_LAUNCH(ctx, sum_partials_kernel, (int)ceil_div((int64_t)nl * tc, 128), 128, 0, partial.p, rb, nl * tc, hbuf.p);
+                sum_partials(ctx, partial.p, rb, nl * tc, hbuf.p);
                 KR_LAUNCH(ctx, entries_accum_kernel, rbk, 128, 0, Hc.p, it1, j, l0, nl, tc, R, hbuf.p, inv.p, mode);
                 KR_LAUNCH(ctx, multi_axpy_kernel, cgrid, COL_THREADS, 0, pc, nl, W.p(), n, tc, hbuf.p);
             }
@@ -262,7 +262,7 @@ inline EntriesResult entries_run(kr_ctx* ctx, const kr_matrix* M, const std::vec
         gs_pass(0);
         gs_pass(1);
         KR_LAUNCH(ctx, colnorm2_kernel, cgrid, COL_THREADS, 0, W.p(), n, partial.p, tc);
-        KR_LAUNCH(ctx, sum_partials_kernel, sb, 128, 0, partial.p, rb, tc, hbuf.p);
+        sum_partials(ctx, partial.p, rb, tc, hbuf.p);
         KR_LAUNCH(ctx, entries_accum_kernel, rbk, 128, 0, Hc.p, it1, j, 0, 0, tc, R, hbuf.p, inv.p, 2);
         KR_LAUNCH(ctx, colscale_kernel, cgrid, COL_THREADS, 0, W.p(), n, tc, inv.p);
         gs_pass(3);

@@ -366,13 +366,13 @@ inline void pairs_run_chunk(kr_ctx* ctx, const kr_matrix* M, const int64_t* E_de
         EpiGram2 epi;
         epi.Y = Y; epi.P = P; epi.C = C; epi.partial = partial.p; epi.ncand = ncp;
         launch_spmm(ctx, A, C, panels, epi, nullptr, cols);
-        KR_LAUNCH(ctx, sum_partials_kernel, sb8, 128, 0, partial.p, A.ntiles, ncp * 8, Gsum.p);
+        sum_partials(ctx, partial.p, A.ntiles, ncp * 8, Gsum.p);
         KR_LAUNCH(ctx, pair_coef1_kernel, cb, 128, 0, st, Gsum.p, first);
         KR_LAUNCH(ctx, pair_update_kernel<0>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ncp, partial.p);
-        KR_LAUNCH(ctx, sum_partials_kernel, sb8, 128, 0, partial.p, rb, ncp * 8, Gsum.p);
+        sum_partials(ctx, partial.p, rb, ncp * 8, Gsum.p);
         KR_LAUNCH(ctx, pair_coef2_kernel, cb, 128, 0, st, Gsum.p, first);
         KR_LAUNCH(ctx, pair_update_kernel<1>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ncp, partial.p);
-        KR_LAUNCH(ctx, sum_partials_kernel, sb4, 128, 0, partial.p, rb, ncp * 4, Gsum.p);
+        sum_partials(ctx, partial.p, rb, ncp * 4, Gsum.p);
         const int nn = 2 * j;
         const size_t smem = (size_t)(2 * nn * (nn | 1) + 2 * nn) * sizeof(double);
         if (smem > JAC_SMEM_LIMIT)

@@ -27,7 +27,7 @@ inline SlqResult slq_run(kr_ctx* ctx, const kr_matrix* M, PanelBuf& Z, int m, in
     B2.buf.zero();
     const int rb = col_row_blocks(n);
     const int nparts = std::max(rb, A.ntiles);
-    DevBuf<double> partial(ctx, (size_t)nparts * tc);
+    DevBuf<double> partial(ctx, (size_t)nparts * tc), sums(ctx, tc);
     DevBuf<double> scal(ctx, (size_t)tc * 7);         // s1, s0, beta_prev, coef[3], nrm2
     DevBuf<double> alpha(ctx, (size_t)m * tc), beta(ctx, (size_t)m * tc), vals(ctx, tc);
     scal.zero();
@@ -43,7 +43,8 @@ inline SlqResult slq_run(kr_ctx* ctx, const kr_matrix* M, PanelBuf& Z, int m, in
 
     dim3 cgrid((unsigned)rb, (unsigned)panels);
     KR_LAUNCH(ctx, colnorm2_kernel, cgrid, COL_THREADS, 0, Z.p(), n, partial.p, tc);
-    KR_LAUNCH(ctx, slq_init_kernel, sb, 128, 0, partial.p, rb, tc, st, nrm2);
+    sum_partials(ctx, partial.p, rb, tc, sums.p);
+    KR_LAUNCH(ctx, slq_init_kernel, sb, 128, 0, sums.p, tc, st, nrm2);
 
     double* U1 = Z.p();
     double* U0 = B2.p();
@@ -54,10 +55,12 @@ inline SlqResult slq_run(kr_ctx* ctx, const kr_matrix* M, PanelBuf& Z, int m, in
         epi.partial = partial.p;
         epi.total_cols = tc;
         launch_spmm(ctx, A, U1, panels, epi, nullptr, cols);
-        KR_LAUNCH(ctx, slq_alpha_kernel, sb, 128, 0, partial.p, A.ntiles, tc, st, j);
+        sum_partials(ctx, partial.p, A.ntiles, tc, sums.p);
+        KR_LAUNCH(ctx, slq_alpha_kernel, sb, 128, 0, sums.p, tc, st, j);
         KR_LAUNCH(ctx, combine3_norm_kernel, cgrid, COL_THREADS, 0, Y.p(), U1, U0, U0, n, st.coef, tc,
                   partial.p);
-        KR_LAUNCH(ctx, slq_beta_kernel, sb, 128, 0, partial.p, rb, tc, st, j);
+        sum_partials(ctx, partial.p, rb, tc, sums.p);
+        KR_LAUNCH(ctx, slq_beta_kernel, sb, 128, 0, sums.p, tc, st, j);
         std::swap(U0, U1);
     }
     KR_LAUNCH(ctx, slq_quadrature_kernel, (int)ceil_div(cols, 64), 64, 0, alpha.p, beta.p, nrm2, m, cols,

@@ -6,9 +6,12 @@
 // of X per panel: four lanes x one 128-bit load.  A panel of X (64 MB at n = 1M) is what must stay
 // L2-resident while the CSR arrays stream past it; blockIdx.y (slow index) walks the panels.
 //
-// Scheduling: one CTA (8 warps) per RowTile (csr.cuh); inside a tile every row gets L = 4/8/16/32
-// lanes (L/4 nonzeros in flight per step, 4-way unrolled), partial sums are folded with
-// warp shuffles in a fixed order, so results are bit-reproducible run to run.
+// Scheduling: one CTA (8 warps) per RowTile (csr.cuh).  The CTA first streams the tile's row
+// pointers / row numbers / column indices (and values) into shared memory with coalesced loads, so
+// the only dependent global loads left are the X gathers; inside a tile every row gets L = 4/8/16/32
+// lanes (L/4 nonzeros in flight per step, 4-way unrolled).  Rows with >= 1024 nonzeros get a whole
+// CTA.  Partial sums are folded with warp shuffles / shared memory in a fixed order, so results are
+// bit-reproducible run to run (no float atomics).
 //
 // HBM roofline: algorithmic bytes per launch = 12*nnz + 4*(n+1) + 16*n*k.
 #pragma once
@@ -83,11 +86,14 @@ struct EpiPlain {
         Y += q * stride;
         X += q * stride;
     }
+    double2 xr;
+    __device__ __forceinline__ void pre(int r, int sub) {
+        if (mu != 0.0) xr = *reinterpret_cast<const double2*>(X + (int64_t)r * PW + sub * 2);
+    }
     __device__ __forceinline__ void row(int r, int sub, double2 y, unsigned) {
         if (mu != 0.0) {
-            double2 x = *reinterpret_cast<const double2*>(X + (int64_t)r * PW + sub * 2);
-            y.x -= mu * x.x;
-            y.y -= mu * x.y;
+            y.x -= mu * xr.x;
+            y.y -= mu * xr.y;
         }
         y.x *= alpha;
         y.y *= alpha;
@@ -108,10 +114,13 @@ struct EpiDot {
         X += q * stride;
         acc[0] = acc[1] = 0.0;
     }
+    double2 xr;
+    __device__ __forceinline__ void pre(int r, int sub) {
+        xr = *reinterpret_cast<const double2*>(X + (int64_t)r * PW + sub * 2);
+    }
     __device__ __forceinline__ void row(int r, int sub, double2 y, unsigned) {
-        double2 x = *reinterpret_cast<const double2*>(X + (int64_t)r * PW + sub * 2);
-        acc[0] += x.x * y.x;
-        acc[1] += x.y * y.y;
+        acc[0] += xr.x * y.x;
+        acc[1] += xr.y * y.y;
         st_stream(Y + (int64_t)r * PW + sub * 2, y);
     }
     __device__ __forceinline__ void finish(int tile, int panel, double* smem) {
@@ -140,11 +149,17 @@ struct EpiGram2 {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.0;
     }
+    double2 cr, pr;
+    __device__ __forceinline__ void pre(int r, int sub) {
+        const int64_t o = (int64_t)r * PW + sub * 2;
+        cr = *reinterpret_cast<const double2*>(C + o);
+        if (P) pr = *reinterpret_cast<const double2*>(P + o);
+    }
     __device__ __forceinline__ void row(int r, int sub, double2 y, unsigned) {
         const int64_t o = (int64_t)r * PW + sub * 2;
-        double2 c = *reinterpret_cast<const double2*>(C + o);
+        const double2 c = cr;
         if (P) {
-            double2 p = *reinterpret_cast<const double2*>(P + o);
+            const double2 p = pr;
             acc[0] += p.x * y.x; acc[1] += p.x * y.y;
             acc[2] += p.y * y.x; acc[3] += p.y * y.y;
         }
@@ -180,16 +195,21 @@ struct EpiTaylor {
         rab += q * (stride / PW);
         raf += q * (stride / PW);
     }
+    double2 xr, fr;
+    __device__ __forceinline__ void pre(int r, int sub) {
+        const int64_t o = (int64_t)r * PW + sub * 2;
+        if (mu != 0.0) xr = *reinterpret_cast<const double2*>(Bo + o);
+        fr = *reinterpret_cast<const double2*>(F + o);
+    }
     __device__ __forceinline__ void row(int r, int sub, double2 y, unsigned m) {
         const int64_t o = (int64_t)r * PW + sub * 2;
         if (mu != 0.0) {
-            double2 x = *reinterpret_cast<const double2*>(Bo + o);
-            y.x -= mu * x.x;
-            y.y -= mu * x.y;
+            y.x -= mu * xr.x;
+            y.y -= mu * xr.y;
         }
         y.x *= coef;
         y.y *= coef;
-        double2 f = *reinterpret_cast<const double2*>(F + o);
+        double2 f = fr;
         f.x += y.x;
         f.y += y.y;
         *reinterpret_cast<double2*>(F + o) = f;
@@ -210,44 +230,52 @@ struct EpiTaylor {
 };
 
 // ------------------------------------------------------------------------------- kernel
-template <int L, class Epi>
-__device__ __forceinline__ void spmm_tile(const CsrDevView& A, const RowTile t,
-                                          const double* __restrict__ Xp, Epi& epi) {
+struct SpmmSmem {
+    int rp[SPMM_MAX_ROWS + 1];     // tile-relative row pointers
+    int rid[SPMM_MAX_ROWS];        // original row numbers
+    int col[SPMM_CAP];
+};
+
+// Multi-row tile: indices are already staged in shared memory; every row gets L lanes.
+template <int L, bool HAS_VAL, class Epi>
+__device__ __forceinline__ void spmm_tile(const RowTile t, const SpmmSmem& sm, const double* __restrict__ sval,
+                                          const double* __restrict__ Xp, double uval, Epi& epi) {
     constexpr int S = L / 4;            // nonzero slots per row per step
     constexpr int RPW = 32 / L;         // rows per warp per pass
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 3;
     const int slot = (lane % L) >> 2;
     const int rlocal = lane / L;
-    const bool has_val = A.val != nullptr;
+    const double* xs = Xp + sub * 2;
     for (int base = warp * RPW; base < t.count; base += SPMM_WARPS * RPW) {
         const int rr = base + rlocal;
         const bool valid = rr < t.count;
         int row = 0, p0 = 0, p1 = 0;
         if (valid) {
-            row = __ldg(A.row_order + t.start + rr);
-            p0 = __ldg(A.row_ptr + row);
-            p1 = __ldg(A.row_ptr + row + 1);
+            row = sm.rid[rr];
+            p0 = sm.rp[rr];
+            p1 = sm.rp[rr + 1];
         }
+        const bool emit = valid && slot == 0;
+        if (emit) epi.pre(row, sub);    // row-local operands: issue their loads before the gathers
         double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
-        const double* xs = Xp + sub * 2;
         for (int p = p0 + slot; p < p1; p += 4 * S) {
             const bool b1 = p + S < p1, b2 = p + 2 * S < p1, b3 = p + 3 * S < p1;
-            int c0 = ld_stream(A.col + p);
-            int c1 = b1 ? ld_stream(A.col + p + S) : 0;
-            int c2 = b2 ? ld_stream(A.col + p + 2 * S) : 0;
-            int c3 = b3 ? ld_stream(A.col + p + 3 * S) : 0;
+            const int c0 = sm.col[p];
+            const int c1 = b1 ? sm.col[p + S] : c0;
+            const int c2 = b2 ? sm.col[p + 2 * S] : c0;
+            const int c3 = b3 ? sm.col[p + 3 * S] : c0;
             double v0 = 1.0, v1 = b1 ? 1.0 : 0.0, v2 = b2 ? 1.0 : 0.0, v3 = b3 ? 1.0 : 0.0;
-            if (has_val) {
-                v0 = ld_stream(A.val + p);
-                if (b1) v1 = ld_stream(A.val + p + S);
-                if (b2) v2 = ld_stream(A.val + p + 2 * S);
-                if (b3) v3 = ld_stream(A.val + p + 3 * S);
+            if (HAS_VAL) {
+                v0 = sval[p];
+                if (b1) v1 = sval[p + S];
+                if (b2) v2 = sval[p + 2 * S];
+                if (b3) v3 = sval[p + 3 * S];
             }
-            double2 x0 = ld_x(xs + (int64_t)c0 * PW);
-            double2 x1 = ld_x(xs + (int64_t)c1 * PW);
-            double2 x2 = ld_x(xs + (int64_t)c2 * PW);
-            double2 x3 = ld_x(xs + (int64_t)c3 * PW);
+            const double2 x0 = ld_x(xs + (int64_t)c0 * PW);
+            const double2 x1 = ld_x(xs + (int64_t)c1 * PW);
+            const double2 x2 = ld_x(xs + (int64_t)c2 * PW);
+            const double2 x3 = ld_x(xs + (int64_t)c3 * PW);
             a0.x = fma(v0, x0.x, a0.x); a0.y = fma(v0, x0.y, a0.y);
             a1.x = fma(v1, x1.x, a1.x); a1.y = fma(v1, x1.y, a1.y);
             a2.x = fma(v2, x2.x, a2.x); a2.y = fma(v2, x2.y, a2.y);
@@ -260,35 +288,100 @@ __device__ __forceinline__ void spmm_tile(const CsrDevView& A, const RowTile t,
             acc.x += o.x;
             acc.y += o.y;
         }
-        if (!has_val) {
-            acc.x *= A.uval;
-            acc.y *= A.uval;
+        if (!HAS_VAL) {
+            acc.x *= uval;
+            acc.y *= uval;
         }
-        const bool emit = valid && slot == 0;
         const unsigned m = __ballot_sync(0xffffffffu, emit);
         if (emit) epi.row(row, sub, acc, m);
     }
 }
 
+// One long row processed by the whole CTA: 64 nonzero slots stride the row straight from global
+// memory (coalesced index loads), partial sums meet in shared memory in a fixed order.
+template <bool HAS_VAL, class Epi>
+__device__ __forceinline__ void spmm_long_row(const CsrDevView& A, const RowTile t, const double* __restrict__ Xp,
+                                              double* red, Epi& epi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 3;
+    const int slot = threadIdx.x >> 2;                 // 0..63
+    constexpr int S = SPMM_THREADS / 4;
+    const int row = __ldg(A.row_order + t.start);
+    const int p0 = __ldg(A.row_ptr + t.start), p1 = __ldg(A.row_ptr + t.start + 1);
+    const bool emit = threadIdx.x < 4;
+    if (emit) epi.pre(row, sub);
+    const double* xs = Xp + sub * 2;
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
+    for (int p = p0 + slot; p < p1; p += 4 * S) {
+        const bool b1 = p + S < p1, b2 = p + 2 * S < p1, b3 = p + 3 * S < p1;
+        const int c0 = ld_stream(A.col + p);
+        const int c1 = b1 ? ld_stream(A.col + p + S) : c0;
+        const int c2 = b2 ? ld_stream(A.col + p + 2 * S) : c0;
+        const int c3 = b3 ? ld_stream(A.col + p + 3 * S) : c0;
+        double v0 = 1.0, v1 = b1 ? 1.0 : 0.0, v2 = b2 ? 1.0 : 0.0, v3 = b3 ? 1.0 : 0.0;
+        if (HAS_VAL) {
+            v0 = ld_stream(A.val + p);
+            if (b1) v1 = ld_stream(A.val + p + S);
+            if (b2) v2 = ld_stream(A.val + p + 2 * S);
+            if (b3) v3 = ld_stream(A.val + p + 3 * S);
+        }
+        const double2 x0 = ld_x(xs + (int64_t)c0 * PW);
+        const double2 x1 = ld_x(xs + (int64_t)c1 * PW);
+        const double2 x2 = ld_x(xs + (int64_t)c2 * PW);
+        const double2 x3 = ld_x(xs + (int64_t)c3 * PW);
+        a0.x = fma(v0, x0.x, a0.x); a0.y = fma(v0, x0.y, a0.y);
+        a1.x = fma(v1, x1.x, a1.x); a1.y = fma(v1, x1.y, a1.y);
+        a2.x = fma(v2, x2.x, a2.x); a2.y = fma(v2, x2.y, a2.y);
+        a3.x = fma(v3, x3.x, a3.x); a3.y = fma(v3, x3.y, a3.y);
+    }
+    double v[2] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y)};
+    cta_reduce_by_sub<2>(v, red);                      // totals in threads 0..3
+    double2 acc = make_double2(v[0], v[1]);
+    if (!HAS_VAL) {
+        acc.x *= A.uval;
+        acc.y *= A.uval;
+    }
+    (void)warp;
+    const unsigned m = __ballot_sync(0xffffffffu, emit);
+    if (emit) epi.row(row, sub, acc, m);
+    __syncthreads();                                   // red[] is reused by epi.finish
+}
+
 // grid = (ntiles, panels); X panel q at X + q*n*8.  `done` (may be null): skip everything if set.
-template <class Epi>
+// Dynamic shared memory: SPMM_CAP doubles for the staged values when the matrix carries values.
+template <class Epi, bool HAS_VAL>
 __global__ void __launch_bounds__(SPMM_THREADS)
 spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t panel_stride,
             const int* __restrict__ done) {
     if (done && *done) return;
-    __shared__ double smem[SPMM_WARPS * 4 * 8];
+    __shared__ double red[SPMM_WARPS * 4 * 8];
+    __shared__ SpmmSmem sm;
+    extern __shared__ double sval[];
     const int tile = blockIdx.x, panel = blockIdx.y;
     const RowTile t = A.tiles[tile];
     Epi epi = epi_proto;
     epi.init(panel, panel_stride);
     const double* Xp = X + (int64_t)panel * panel_stride;
-    switch (t.lanes_log2) {
-        case 2: spmm_tile<4>(A, t, Xp, epi); break;
-        case 3: spmm_tile<8>(A, t, Xp, epi); break;
-        case 4: spmm_tile<16>(A, t, Xp, epi); break;
-        default: spmm_tile<32>(A, t, Xp, epi); break;
+    if (t.lanes_log2 == 6) {
+        spmm_long_row<HAS_VAL>(A, t, Xp, red, epi);
+    } else {
+        // stage the tile's row pointers, row numbers and column indices (coalesced streams)
+        const int pb = __ldg(A.row_ptr + t.start);
+        for (int i = threadIdx.x; i <= t.count; i += SPMM_THREADS) sm.rp[i] = __ldg(A.row_ptr + t.start + i) - pb;
+        for (int i = threadIdx.x; i < t.count; i += SPMM_THREADS) sm.rid[i] = __ldg(A.row_order + t.start + i);
+        const int nz = __ldg(A.row_ptr + t.start + t.count) - pb;
+        for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) sm.col[p] = ld_stream(A.col + pb + p);
+        if (HAS_VAL)
+            for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + p);
+        __syncthreads();
+        switch (t.lanes_log2) {
+            case 2: spmm_tile<4, HAS_VAL>(t, sm, sval, Xp, A.uval, epi); break;
+            case 3: spmm_tile<8, HAS_VAL>(t, sm, sval, Xp, A.uval, epi); break;
+            case 4: spmm_tile<16, HAS_VAL>(t, sm, sval, Xp, A.uval, epi); break;
+            default: spmm_tile<32, HAS_VAL>(t, sm, sval, Xp, A.uval, epi); break;
+        }
     }
-    epi.finish(tile, panel, smem);
+    epi.finish(tile, panel, red);
 }
 
 // Host-side launcher.  Epilogues carry panel-0 pointers; init() advances them to the CTA's panel.
@@ -303,7 +396,17 @@ inline void launch_spmm(kr_ctx* ctx, const CsrDev& A, const double* X, int panel
         KR_CUDA(cudaEventRecord(e0, ctx->stream));
     }
     dim3 grid((unsigned)A.ntiles, (unsigned)panels);
-    spmm_kernel<Epi><<<grid, SPMM_THREADS, 0, ctx->stream>>>(A.view(), X, epi, (int64_t)A.n * PW, done);
+    if (A.pattern_only) {
+        spmm_kernel<Epi, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(A.view(), X, epi, (int64_t)A.n * PW, done);
+    } else {
+        static bool attr_set = false;           // one flag per Epi instantiation
+        const size_t dyn = SPMM_CAP * sizeof(double);
+        if (!attr_set) {
+            KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            attr_set = true;
+        }
+        spmm_kernel<Epi, true><<<grid, SPMM_THREADS, dyn, ctx->stream>>>(A.view(), X, epi, (int64_t)A.n * PW, done);
+    }
     check_launch(ctx, "spmm_kernel");
     if (ctx->timing) {
         KR_CUDA(cudaEventRecord(e1, ctx->stream));
