@@ -156,7 +156,7 @@ inline void upload_csr(kr_ctx* ctx, const CsrHost& H, CsrDev& D) {
     }
     // ---- tiles: runs of one lane class, nonzeros <= SPMM_CAP, rows <= SPMM_MAX_ROWS; long rows alone
     auto lane_class = [](int len) {
-        return len >= SPMM_LONG_ROW ? 6 : len >= 64 ? 5 : len >= 20 ? 4 : len >= 7 ? 3 : 2;
+        return len >= SPMM_LONG_ROW ? 6 : len >= 256 ? 5 : len >= 64 ? 4 : len >= 16 ? 3 : 2;
     };
     std::vector<RowTile> tiles;
     int64_t i = 0;

@@ -9,8 +9,8 @@
 // Scheduling: one CTA (8 warps) per RowTile (csr.cuh).  The CTA first streams the tile's row
 // pointers / row numbers / column indices (and values) into shared memory with coalesced loads, so
 // the only dependent global loads left are the X gathers; inside a tile every row gets L = 4/8/16/32
-// lanes (L/4 nonzeros in flight per step, 4-way unrolled).  Rows with >= 1024 nonzeros get a whole
-// CTA.  Partial sums are folded with warp shuffles / shared memory in a fixed order, so results are
+// lanes and every lane issues U (4 or 8) independent 128-bit gathers before its first FMA.  Rows with
+// >= 1024 nonzeros get a whole CTA.  Partial sums are folded with warp shuffles / shared memory in a fixed order, so results are
 // bit-reproducible run to run (no float atomics).
 //
 // HBM roofline: algorithmic bytes per launch = 12*nnz + 4*(n+1) + 16*n*k.
@@ -22,6 +22,7 @@ namespace kr {
 constexpr int PW = 8;              // panel width (columns)
 constexpr int SPMM_THREADS = 256;  // 8 warps
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
+constexpr int SPMM_DEFAULT_UNROLL = 8;  // independent gathers per lane before the first FMA
 
 struct PanelBlock {                // non-owning view of a panel-major block
     double* p;
@@ -230,17 +231,51 @@ struct EpiTaylor {
 };
 
 // ------------------------------------------------------------------------------- kernel
-struct SpmmSmem {
-    int rp[SPMM_MAX_ROWS + 1];     // tile-relative row pointers
-    int rid[SPMM_MAX_ROWS];        // original row numbers
-    int col[SPMM_CAP];
-};
+// dynamic shared memory carve-up (bytes): col | rp | rid | [val]
+constexpr size_t SPMM_SMEM_PATTERN = SPMM_CAP * sizeof(int) + (SPMM_MAX_ROWS + 1 + SPMM_MAX_ROWS + 3) * sizeof(int);
+constexpr size_t SPMM_SMEM_VALUED = SPMM_SMEM_PATTERN + SPMM_CAP * sizeof(double);
+
+// One lane's share of a row: nonzeros p_first, p_first+stride, ... < p_end (tile-relative, indices in
+// shared memory).  U independent 16-byte gathers are issued back to back before the first FMA, so a
+// lane keeps U row-tiles of X in flight (measured: a cp.async ring that parks the in-flight data in
+// shared memory instead of registers is SLOWER here - it triples the L1TEX data-pipe wavefronts, the
+// unit that limits this kernel; profiles/r01_d_*).
+template <bool HAS_VAL, int U>
+__device__ __forceinline__ double2 gather_accumulate(int p_first, int p_end, int stride, const int* __restrict__ scol,
+                                                     const double* __restrict__ sval, const double* __restrict__ xs) {
+    double2 acc0 = make_double2(0.0, 0.0), acc1 = acc0;
+    for (int p = p_first; p < p_end; p += U * stride) {
+        double2 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = p + u * stride;
+            const int c = scol[q < p_end ? q : p];
+            x[u] = ld_x(xs + (int64_t)c * PW);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = p + u * stride;
+            const double v = q < p_end ? (HAS_VAL ? sval[q] : 1.0) : 0.0;
+            if (u & 1) {
+                acc1.x = fma(v, x[u].x, acc1.x);
+                acc1.y = fma(v, x[u].y, acc1.y);
+            } else {
+                acc0.x = fma(v, x[u].x, acc0.x);
+                acc0.y = fma(v, x[u].y, acc0.y);
+            }
+        }
+    }
+    acc0.x += acc1.x;
+    acc0.y += acc1.y;
+    return acc0;
+}
 
 // Multi-row tile: indices are already staged in shared memory; every row gets L lanes.
-template <int L, bool HAS_VAL, class Epi>
-__device__ __forceinline__ void spmm_tile(const RowTile t, const SpmmSmem& sm, const double* __restrict__ sval,
+template <int L, bool HAS_VAL, int U, class Epi>
+__device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict__ srp, const int* __restrict__ srid,
+                                          const int* __restrict__ scol, const double* __restrict__ sval,
                                           const double* __restrict__ Xp, double uval, Epi& epi) {
-    constexpr int S = L / 4;            // nonzero slots per row per step
+    constexpr int S = L / 4;            // nonzero slots per row
     constexpr int RPW = 32 / L;         // rows per warp per pass
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 3;
@@ -252,36 +287,13 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const SpmmSmem& sm, c
         const bool valid = rr < t.count;
         int row = 0, p0 = 0, p1 = 0;
         if (valid) {
-            row = sm.rid[rr];
-            p0 = sm.rp[rr];
-            p1 = sm.rp[rr + 1];
+            row = srid[rr];
+            p0 = srp[rr];
+            p1 = srp[rr + 1];
         }
         const bool emit = valid && slot == 0;
         if (emit) epi.pre(row, sub);    // row-local operands: issue their loads before the gathers
-        double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
-        for (int p = p0 + slot; p < p1; p += 4 * S) {
-            const bool b1 = p + S < p1, b2 = p + 2 * S < p1, b3 = p + 3 * S < p1;
-            const int c0 = sm.col[p];
-            const int c1 = b1 ? sm.col[p + S] : c0;
-            const int c2 = b2 ? sm.col[p + 2 * S] : c0;
-            const int c3 = b3 ? sm.col[p + 3 * S] : c0;
-            double v0 = 1.0, v1 = b1 ? 1.0 : 0.0, v2 = b2 ? 1.0 : 0.0, v3 = b3 ? 1.0 : 0.0;
-            if (HAS_VAL) {
-                v0 = sval[p];
-                if (b1) v1 = sval[p + S];
-                if (b2) v2 = sval[p + 2 * S];
-                if (b3) v3 = sval[p + 3 * S];
-            }
-            const double2 x0 = ld_x(xs + (int64_t)c0 * PW);
-            const double2 x1 = ld_x(xs + (int64_t)c1 * PW);
-            const double2 x2 = ld_x(xs + (int64_t)c2 * PW);
-            const double2 x3 = ld_x(xs + (int64_t)c3 * PW);
-            a0.x = fma(v0, x0.x, a0.x); a0.y = fma(v0, x0.y, a0.y);
-            a1.x = fma(v1, x1.x, a1.x); a1.y = fma(v1, x1.y, a1.y);
-            a2.x = fma(v2, x2.x, a2.x); a2.y = fma(v2, x2.y, a2.y);
-            a3.x = fma(v3, x3.x, a3.x); a3.y = fma(v3, x3.y, a3.y);
-        }
-        double2 acc = make_double2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+        double2 acc = gather_accumulate<HAS_VAL, U>(p0 + slot, p1, S, scol, sval, xs);
 #pragma unroll
         for (int off = 4; off < L; off <<= 1) {
             double2 o = shfl_xor2(acc, off);
@@ -297,88 +309,65 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const SpmmSmem& sm, c
     }
 }
 
-// One long row processed by the whole CTA: 64 nonzero slots stride the row straight from global
-// memory (coalesced index loads), partial sums meet in shared memory in a fixed order.
-template <bool HAS_VAL, class Epi>
-__device__ __forceinline__ void spmm_long_row(const CsrDevView& A, const RowTile t, const double* __restrict__ Xp,
-                                              double* red, Epi& epi) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane & 3;
-    const int slot = threadIdx.x >> 2;                 // 0..63
-    constexpr int S = SPMM_THREADS / 4;
-    const int row = __ldg(A.row_order + t.start);
-    const int p0 = __ldg(A.row_ptr + t.start), p1 = __ldg(A.row_ptr + t.start + 1);
-    const bool emit = threadIdx.x < 4;
-    if (emit) epi.pre(row, sub);
-    const double* xs = Xp + sub * 2;
-    double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
-    for (int p = p0 + slot; p < p1; p += 4 * S) {
-        const bool b1 = p + S < p1, b2 = p + 2 * S < p1, b3 = p + 3 * S < p1;
-        const int c0 = ld_stream(A.col + p);
-        const int c1 = b1 ? ld_stream(A.col + p + S) : c0;
-        const int c2 = b2 ? ld_stream(A.col + p + 2 * S) : c0;
-        const int c3 = b3 ? ld_stream(A.col + p + 3 * S) : c0;
-        double v0 = 1.0, v1 = b1 ? 1.0 : 0.0, v2 = b2 ? 1.0 : 0.0, v3 = b3 ? 1.0 : 0.0;
-        if (HAS_VAL) {
-            v0 = ld_stream(A.val + p);
-            if (b1) v1 = ld_stream(A.val + p + S);
-            if (b2) v2 = ld_stream(A.val + p + 2 * S);
-            if (b3) v3 = ld_stream(A.val + p + 3 * S);
-        }
-        const double2 x0 = ld_x(xs + (int64_t)c0 * PW);
-        const double2 x1 = ld_x(xs + (int64_t)c1 * PW);
-        const double2 x2 = ld_x(xs + (int64_t)c2 * PW);
-        const double2 x3 = ld_x(xs + (int64_t)c3 * PW);
-        a0.x = fma(v0, x0.x, a0.x); a0.y = fma(v0, x0.y, a0.y);
-        a1.x = fma(v1, x1.x, a1.x); a1.y = fma(v1, x1.y, a1.y);
-        a2.x = fma(v2, x2.x, a2.x); a2.y = fma(v2, x2.y, a2.y);
-        a3.x = fma(v3, x3.x, a3.x); a3.y = fma(v3, x3.y, a3.y);
-    }
-    double v[2] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y)};
-    cta_reduce_by_sub<2>(v, red);                      // totals in threads 0..3
-    double2 acc = make_double2(v[0], v[1]);
-    if (!HAS_VAL) {
-        acc.x *= A.uval;
-        acc.y *= A.uval;
-    }
-    (void)warp;
-    const unsigned m = __ballot_sync(0xffffffffu, emit);
-    if (emit) epi.row(row, sub, acc, m);
-    __syncthreads();                                   // red[] is reused by epi.finish
-}
-
 // grid = (ntiles, panels); X panel q at X + q*n*8.  `done` (may be null): skip everything if set.
-// Dynamic shared memory: SPMM_CAP doubles for the staged values when the matrix carries values.
-template <class Epi, bool HAS_VAL>
-__global__ void __launch_bounds__(SPMM_THREADS)
+template <class Epi, bool HAS_VAL, int U>
+__global__ void __launch_bounds__(SPMM_THREADS, 4)
 spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t panel_stride,
             const int* __restrict__ done) {
     if (done && *done) return;
     __shared__ double red[SPMM_WARPS * 4 * 8];
-    __shared__ SpmmSmem sm;
-    extern __shared__ double sval[];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    int* scol = reinterpret_cast<int*>(dyn_smem);
+    int* srp = scol + SPMM_CAP;
+    int* srid = srp + SPMM_MAX_ROWS + 1;
+    double* sval = reinterpret_cast<double*>(dyn_smem + SPMM_SMEM_PATTERN);
     const int tile = blockIdx.x, panel = blockIdx.y;
     const RowTile t = A.tiles[tile];
     Epi epi = epi_proto;
     epi.init(panel, panel_stride);
     const double* Xp = X + (int64_t)panel * panel_stride;
+    const int pb = __ldg(A.row_ptr + t.start);
+    const int nz = __ldg(A.row_ptr + t.start + t.count) - pb;
     if (t.lanes_log2 == 6) {
-        spmm_long_row<HAS_VAL>(A, t, Xp, red, epi);
+        // one long row, whole CTA: stage the indices chunk by chunk, 64 nonzero slots stride each chunk
+        const int sub = threadIdx.x & 3, slot = threadIdx.x >> 2;
+        const int row = __ldg(A.row_order + t.start);
+        const bool emit = threadIdx.x < 4;
+        if (emit) epi.pre(row, sub);
+        double v[2] = {0.0, 0.0};
+        for (int c0 = 0; c0 < nz; c0 += SPMM_CAP) {
+            const int cn = min(SPMM_CAP, nz - c0);
+            __syncthreads();
+            for (int p = threadIdx.x; p < cn; p += SPMM_THREADS) scol[p] = ld_stream(A.col + pb + c0 + p);
+            if (HAS_VAL)
+                for (int p = threadIdx.x; p < cn; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + c0 + p);
+            __syncthreads();
+            double2 a = gather_accumulate<HAS_VAL, U>(slot, cn, SPMM_THREADS / 4, scol, sval, Xp + sub * 2);
+            v[0] += a.x;
+            v[1] += a.y;
+        }
+        cta_reduce_by_sub<2>(v, red);                  // totals in threads 0..3
+        double2 acc = make_double2(v[0], v[1]);
+        if (!HAS_VAL) {
+            acc.x *= A.uval;
+            acc.y *= A.uval;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, emit);
+        if (emit) epi.row(row, sub, acc, m);
+        __syncthreads();                               // red[] is reused by epi.finish
     } else {
         // stage the tile's row pointers, row numbers and column indices (coalesced streams)
-        const int pb = __ldg(A.row_ptr + t.start);
-        for (int i = threadIdx.x; i <= t.count; i += SPMM_THREADS) sm.rp[i] = __ldg(A.row_ptr + t.start + i) - pb;
-        for (int i = threadIdx.x; i < t.count; i += SPMM_THREADS) sm.rid[i] = __ldg(A.row_order + t.start + i);
-        const int nz = __ldg(A.row_ptr + t.start + t.count) - pb;
-        for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) sm.col[p] = ld_stream(A.col + pb + p);
+        for (int i = threadIdx.x; i <= t.count; i += SPMM_THREADS) srp[i] = __ldg(A.row_ptr + t.start + i) - pb;
+        for (int i = threadIdx.x; i < t.count; i += SPMM_THREADS) srid[i] = __ldg(A.row_order + t.start + i);
+        for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) scol[p] = ld_stream(A.col + pb + p);
         if (HAS_VAL)
             for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + p);
         __syncthreads();
         switch (t.lanes_log2) {
-            case 2: spmm_tile<4, HAS_VAL>(t, sm, sval, Xp, A.uval, epi); break;
-            case 3: spmm_tile<8, HAS_VAL>(t, sm, sval, Xp, A.uval, epi); break;
-            case 4: spmm_tile<16, HAS_VAL>(t, sm, sval, Xp, A.uval, epi); break;
-            default: spmm_tile<32, HAS_VAL>(t, sm, sval, Xp, A.uval, epi); break;
+            case 2: spmm_tile<4, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
+            case 3: spmm_tile<8, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
+            case 4: spmm_tile<16, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
+            default: spmm_tile<32, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
         }
     }
     epi.finish(tile, panel, red);
@@ -396,16 +385,24 @@ inline void launch_spmm(kr_ctx* ctx, const CsrDev& A, const double* X, int panel
         KR_CUDA(cudaEventRecord(e0, ctx->stream));
     }
     dim3 grid((unsigned)A.ntiles, (unsigned)panels);
+    static bool attr_set = false;               // one flag per Epi instantiation
+    static int variant = 4;
+    if (!attr_set) {
+        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_PATTERN));
+        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_VALUED));
+        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_PATTERN));
+        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_VALUED));
+        const char* e = getenv("KR_SPMM_UNROLL");   // tuning knob: gathers in flight per lane (4 or 8)
+        variant = (e && atoi(e) == 8) ? 8 : (e && atoi(e) == 4) ? 4 : SPMM_DEFAULT_UNROLL;
+        attr_set = true;
+    }
+    const int64_t ps = (int64_t)A.n * PW;
     if (A.pattern_only) {
-        spmm_kernel<Epi, false><<<grid, SPMM_THREADS, 0, ctx->stream>>>(A.view(), X, epi, (int64_t)A.n * PW, done);
+        if (variant == 8) spmm_kernel<Epi, false, 8><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done);
+        else spmm_kernel<Epi, false, 4><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done);
     } else {
-        static bool attr_set = false;           // one flag per Epi instantiation
-        const size_t dyn = SPMM_CAP * sizeof(double);
-        if (!attr_set) {
-            KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            attr_set = true;
-        }
-        spmm_kernel<Epi, true><<<grid, SPMM_THREADS, dyn, ctx->stream>>>(A.view(), X, epi, (int64_t)A.n * PW, done);
+        if (variant == 8) spmm_kernel<Epi, true, 8><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done);
+        else spmm_kernel<Epi, true, 4><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done);
     }
     check_launch(ctx, "spmm_kernel");
     if (ctx->timing) {

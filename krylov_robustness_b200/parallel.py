@@ -1,0 +1,92 @@
+"""Multi-GPU sharding of the path: A is replicated on every GPU, the independent units
+(probe columns, candidate edges, distinct row indices) are split across ranks, and ONE tiny collective
+per outer step brings the scalars together (all-reduce of the partial trace, all-gather of the
+candidate scores).  One process per GPU, torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+
+Nothing here computes: the per-rank work is a callable (the device entry points in production, the
+oracle in the world_size-2 gloo tests), so the sharding / gathering / tie-breaking logic is testable
+without a GPU.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _device():
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def shard_bounds(n_items, rank=None, world=None):
+    """Contiguous, balanced split: items [lo, hi) belong to `rank`."""
+    r, w = _world()
+    rank = r if rank is None else rank
+    world = w if world is None else world
+    base, rem = divmod(int(n_items), world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum(value):
+    """Sum of a Python float over ranks (the single all-reduce of the trace / objective scalars)."""
+    _, world = _world()
+    if world == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_device())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def allgather_concat(local, n_total):
+    """Concatenate per-rank float64 vectors (shards of shard_bounds order) into the full vector."""
+    _, world = _world()
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if world == 1:
+        return local
+    cap = -(-int(n_total) // world)
+    buf = torch.zeros(cap, dtype=torch.float64, device=_device())
+    buf[:local.size] = torch.from_numpy(local).to(buf.device)
+    out = [torch.zeros(cap, dtype=torch.float64, device=buf.device) for _ in range(world)]
+    dist.all_gather(out, buf)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, r, world)
+        parts.append(out[r][:hi - lo].cpu().numpy())
+    return np.concatenate(parts)
+
+
+def sharded_edge_scores(score_fn, E):
+    """Scores for ALL candidate edges E (k x 2), every rank scoring only its contiguous shard with
+    `score_fn(E_shard) -> vector`, followed by one all-gather.  Every rank returns the identical full
+    vector, so the reference's first-wins arg-min / arg-max (functions/krylov_miobi.m:112-124) picks
+    the same edge everywhere."""
+    E = np.atleast_2d(np.asarray(E))
+    lo, hi = shard_bounds(E.shape[0])
+    local = np.asarray(score_fn(E[lo:hi]), dtype=np.float64) if hi > lo else np.zeros(0)
+    return allgather_concat(local, E.shape[0])
+
+
+def make_sharded_scorer(fun="exp"):
+    """scorer(M, E, b_offdiag, tol, it) for functions.greedy_krylov / krylov_miobi that splits the
+    candidates across ranks (device path on each rank)."""
+    from . import functions as F
+
+    def scorer(M, E, b_offdiag, tol, it):
+        return sharded_edge_scores(lambda Es: F.trace_fun_update_edges(M, Es, b_offdiag, tol, it, fun)[0], E)
+    return scorer
+
+
+def sharded_probe_trace(local_sum_fn, k_total):
+    """Hutchinson / SLQ estimate over k_total probe columns split across ranks:
+    `local_sum_fn(lo, hi)` returns the SUM of the per-probe values of columns [lo, hi); the result is
+    the global mean (one all-reduce of one double)."""
+    lo, hi = shard_bounds(k_total)
+    s = float(local_sum_fn(lo, hi)) if hi > lo else 0.0
+    return allreduce_sum(s) / float(k_total)
