@@ -1,0 +1,30 @@
+function [edges, rob, A_new] = krylov_miobi(A, k, E, tol, it, poles, debug, miobi, rescale)
+% Drop-in for functions/krylov_miobi.m: the candidate loop (:76-99) is ONE batched device call
+% (kr_trace_fun_update_edges); selection and the edge update follow the reference (:112-137).
+if ~issymmetric(A), error('KRYLOV_MIOBI:: Adjacency matrix should be symmetric'); end
+if ~exist('tol', 'var'), tol = 1e-12; end
+if ~exist('it', 'var'), it = min(100, size(A, 1)); end
+if ~exist('miobi', 'var'), miobi = 'break'; end
+if ~exist('rescale', 'var'), rescale = 1; end
+if ~exist('E', 'var') || isempty(E)
+    [t1, t2] = find(A); ind = find(t1 >= t2); E = [t1(ind), t2(ind)];
+end
+if ~strcmp(miobi, 'break') && ~strcmp(miobi, 'make'), error('KRYLOV_MIOBI:: not supported option for miobi'); end
+if strcmp(miobi, 'break') && nnz(A) < 2*k
+    error('KRYLOV_MIOBI:: edges to be removed are more than edges in the network')
+end
+sgn = 1; if strcmp(miobi, 'break'), sgn = -1; end
+rob = 0; edges = zeros(0, 2);
+for j = 1:min(k, size(E, 1))
+    vals = kr_mex('trace_fun_update_edges', A, double(E), sgn/rescale, tol, it, 'exp');
+    if strcmp(miobi, 'break'), mx = [0 inf]; else, mx = [0 -inf]; end
+    for h = 1:size(E, 1)
+        if (sgn < 0 && vals(h) < mx(2)) || (sgn > 0 && vals(h) > mx(2)), mx = [h vals(h)]; end
+    end
+    chosen = E(mx(1), :);
+    E = E([1:mx(1)-1, mx(1)+1:end], :);
+    A(chosen(1), chosen(2)) = (sgn > 0); A(chosen(2), chosen(1)) = (sgn > 0);
+    edges = [edges; chosen]; rob = rob + mx(2);
+end
+A_new = A;
+end

@@ -1,0 +1,223 @@
+/*
+ * kr_mex.c - single MEX gateway (string-dispatched) from MATLAB / GNU Octave into the C ABI of
+ * libkrylov_b200.so (include/krylov_b200.h).  The wrappers in ../matlab/ keep the reference's
+ * function signatures and call   varargout = kr_mex('<op>', args...).
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has neither mex.h nor mkoctfile
+ * (SURVEY.md section 0).  It is a thin marshaller on purpose - every line with arithmetic in it lives
+ * behind the C ABI and is exercised from Python (tests/).  Build where MATLAB/Octave exists:
+ *   mex -I../../include kr_mex.c -L.. -lkrylov_b200          (MATLAB)
+ *   mkoctfile --mex -I../../include kr_mex.c -L.. -lkrylov_b200   (Octave)
+ *
+ * Sparse A arrives as MATLAB CSC (Jc, Ir, Pr).  Every A on this path is symmetric
+ * (functions/greedy_krylov.m:27, functions/krylov_miobi.m:26, functions/fun_and_grad_krylov_fun.m:22),
+ * so its CSC arrays are its CSR arrays and are passed through unchanged; an unsymmetric A is
+ * transposed by the wrapper (A.') before the call.  Device copies of A are cached per mxArray data
+ * pointer + nnz and released by mexAtExit.
+ */
+#include <string.h>
+#include <stdlib.h>
+#include "mex.h"
+#include "krylov_b200.h"
+
+static kr_ctx* g_ctx = NULL;
+#define KR_CACHE 8
+static struct { const void* key; mwSize nnz; kr_matrix* M; } g_cache[KR_CACHE];
+static int g_next = 0;
+
+static void at_exit(void) {
+    int i;
+    for (i = 0; i < KR_CACHE; ++i) if (g_cache[i].M) { kr_matrix_destroy(g_cache[i].M); g_cache[i].M = NULL; }
+    if (g_ctx) { kr_ctx_destroy(g_ctx); g_ctx = NULL; }
+}
+
+static void chk(int status) {
+    if (status != 0) mexErrMsgIdAndTxt("krylov_b200:error", "%s", kr_last_error());
+}
+
+static kr_ctx* ctx(void) {
+    if (!g_ctx) { chk(kr_ctx_create(0, &g_ctx)); mexAtExit(at_exit); }
+    return g_ctx;
+}
+
+static kr_matrix* matrix_of(const mxArray* A) {
+    int i;
+    mwSize n, nnz;
+    const mwIndex *jc, *ir;
+    int64_t *rp, *ci;
+    kr_matrix* M = NULL;
+    if (!mxIsSparse(A) || !mxIsDouble(A)) mexErrMsgTxt("A must be a real sparse double matrix");
+    if (mxGetM(A) != mxGetN(A)) mexErrMsgTxt("The matrix A should be square");
+    n = mxGetN(A); jc = mxGetJc(A); ir = mxGetIr(A); nnz = jc[n];
+    for (i = 0; i < KR_CACHE; ++i)
+        if (g_cache[i].M && g_cache[i].key == (const void*)mxGetPr(A) && g_cache[i].nnz == nnz) return g_cache[i].M;
+    rp = (int64_t*)mxMalloc((n + 1) * sizeof(int64_t));
+    ci = (int64_t*)mxMalloc((nnz ? nnz : 1) * sizeof(int64_t));
+    for (i = 0; i <= (int)n; ++i) rp[i] = (int64_t)jc[i];
+    { mwSize p; for (p = 0; p < nnz; ++p) ci[p] = (int64_t)ir[p]; }
+    chk(kr_matrix_create(ctx(), (int64_t)n, (int64_t)nnz, rp, ci, mxGetPr(A), &M));
+    mxFree(rp); mxFree(ci);
+    if (g_cache[g_next].M) kr_matrix_destroy(g_cache[g_next].M);
+    g_cache[g_next].key = (const void*)mxGetPr(A); g_cache[g_next].nnz = nnz; g_cache[g_next].M = M;
+    g_next = (g_next + 1) % KR_CACHE;
+    return M;
+}
+
+static int fun_of(const mxArray* f) {          /* wrapper passes func2str(f) */
+    char buf[32];
+    mxGetString(f, buf, sizeof buf);
+    if (!strcmp(buf, "exp")) return KR_FUN_EXP;
+    if (!strcmp(buf, "sinh")) return KR_FUN_SINH;
+    if (!strcmp(buf, "cosh")) return KR_FUN_COSH;
+    mexErrMsgTxt("krylov_b200: supported function handles are @exp, @sinh, @cosh");
+    return -1;
+}
+
+static int64_t* to_i64(const mxArray* a, mwSize* count) {
+    mwSize i, k = mxGetNumberOfElements(a);
+    const double* p = mxGetPr(a);
+    int64_t* out = (int64_t*)mxMalloc((k ? k : 1) * sizeof(int64_t));
+    for (i = 0; i < k; ++i) out[i] = (int64_t)p[i];
+    if (count) *count = k;
+    return out;
+}
+
+static mxArray* scalar(double v) { return mxCreateDoubleScalar(v); }
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    char op[64];
+    if (nrhs < 1 || mxGetString(prhs[0], op, sizeof op)) mexErrMsgTxt("kr_mex('<op>', ...)");
+    prhs++; nrhs--;
+
+    if (!strcmp(op, "spmm")) {                                     /* Y = kr_mex('spmm', A, X) */
+        kr_matrix* M = matrix_of(prhs[0]);
+        mwSize n = mxGetM(prhs[1]), k = mxGetN(prhs[1]);
+        plhs[0] = mxCreateDoubleMatrix(n, k, mxREAL);
+        chk(kr_spmm(ctx(), M, (int64_t)k, mxGetPr(prhs[1]), (int64_t)n, mxGetPr(plhs[0]), (int64_t)n));
+    } else if (!strcmp(op, "trace_fun_update")) {                  /* [Xm,iter,lucky] = (A,U,B,tol,it,fun) */
+        kr_matrix* M = matrix_of(prhs[0]);
+        double x; int64_t it; int lucky;
+        chk(kr_trace_fun_update(ctx(), M, (int64_t)mxGetN(prhs[1]), mxGetPr(prhs[1]), (int64_t)mxGetM(prhs[1]),
+                                mxGetPr(prhs[2]), (int64_t)mxGetM(prhs[2]), mxGetScalar(prhs[3]),
+                                (int64_t)mxGetScalar(prhs[4]), fun_of(prhs[5]), &x, &it, &lucky));
+        plhs[0] = scalar(x);
+        if (nlhs > 1) plhs[1] = scalar((double)it);
+        if (nlhs > 2) plhs[2] = mxCreateLogicalScalar(lucky != 0);
+    } else if (!strcmp(op, "trace_fun_update_edges")) {            /* [Xm,iter,lucky] = (A,E,b,tol,it,fun) */
+        kr_matrix* M = matrix_of(prhs[0]);
+        mwSize nE = mxGetM(prhs[1]), i;
+        int64_t* E = to_i64(prhs[1], NULL);
+        int64_t* it = (int64_t*)mxMalloc((nE ? nE : 1) * sizeof(int64_t));
+        int* lk = (int*)mxMalloc((nE ? nE : 1) * sizeof(int));
+        plhs[0] = mxCreateDoubleMatrix(nE, 1, mxREAL);
+        chk(kr_trace_fun_update_edges(ctx(), M, (int64_t)nE, E, mxGetScalar(prhs[2]), mxGetScalar(prhs[3]),
+                                      (int64_t)mxGetScalar(prhs[4]), fun_of(prhs[5]), mxGetPr(plhs[0]), it, lk));
+        if (nlhs > 1) { plhs[1] = mxCreateDoubleMatrix(nE, 1, mxREAL); for (i = 0; i < nE; ++i) mxGetPr(plhs[1])[i] = (double)it[i]; }
+        if (nlhs > 2) { plhs[2] = mxCreateDoubleMatrix(nE, 1, mxREAL); for (i = 0; i < nE; ++i) mxGetPr(plhs[2])[i] = (double)lk[i]; }
+        mxFree(E); mxFree(it); mxFree(lk);
+    } else if (!strcmp(op, "fun_update")) {                        /* [Xm,iter,lucky,Um] = (A,U,B,fun,tol,it,want_basis) */
+        kr_matrix* M = matrix_of(prhs[0]);
+        int64_t dim, it; int lucky, dense;
+        mwSize n = mxGetM(prhs[1]);
+        int want = (int)mxGetScalar(prhs[6]);
+        chk(kr_fun_update(ctx(), M, (int64_t)mxGetN(prhs[1]), mxGetPr(prhs[1]), (int64_t)n, mxGetPr(prhs[2]),
+                          (int64_t)mxGetM(prhs[2]), fun_of(prhs[3]), mxGetScalar(prhs[4]), (int64_t)mxGetScalar(prhs[5]),
+                          want, &dim, &it, &lucky, &dense));
+        plhs[0] = mxCreateDoubleMatrix((mwSize)dim, (mwSize)dim, mxREAL);
+        if (nlhs > 3) plhs[3] = mxCreateDoubleMatrix(n, (mwSize)dim, mxREAL);
+        chk(kr_fun_update_fetch(ctx(), mxGetPr(plhs[0]), dim, nlhs > 3 ? mxGetPr(plhs[3]) : NULL, (int64_t)n));
+        if (nlhs > 1) plhs[1] = scalar((double)it);
+        if (nlhs > 2) plhs[2] = mxCreateLogicalScalar(lucky != 0);
+    } else if (!strcmp(op, "function_multiple_entries")) {         /* [X,iter] = (A,omega,f,tol,it) */
+        kr_matrix* M = matrix_of(prhs[0]);
+        mwSize k = mxGetM(prhs[1]);
+        int64_t* om = to_i64(prhs[1], NULL);
+        int64_t it;
+        plhs[0] = mxCreateDoubleMatrix(k, 1, mxREAL);
+        chk(kr_function_multiple_entries(ctx(), M, (int64_t)k, om, fun_of(prhs[2]), mxGetScalar(prhs[3]),
+                                         (int64_t)mxGetScalar(prhs[4]), mxGetPr(plhs[0]), &it));
+        if (nlhs > 1) plhs[1] = scalar((double)it);
+        mxFree(om);
+    } else if (!strcmp(op, "fun_and_grad")) {                      /* [f,gr] = (X,A,Omega,fun,dfun,dfA,tol,it) */
+        kr_matrix* M = matrix_of(prhs[1]);
+        mwSize k = mxGetM(prhs[2]);
+        int64_t* om = to_i64(prhs[2], NULL);
+        double f;
+        {
+            mxArray* gr = mxCreateDoubleMatrix(k, 1, mxREAL);
+            chk(kr_fun_and_grad_krylov(ctx(), M, (int64_t)k, mxGetPr(prhs[0]), om, fun_of(prhs[3]), fun_of(prhs[4]),
+                                       mxGetPr(prhs[5]), mxGetScalar(prhs[6]), (int64_t)mxGetScalar(prhs[7]), &f, mxGetPr(gr)));
+            plhs[0] = scalar(f);
+            if (nlhs > 1) plhs[1] = gr; else mxDestroyArray(gr);
+        }
+        mxFree(om);
+    } else if (!strcmp(op, "normest")) {                           /* [e,cnt] = (A,tol) */
+        double e; int64_t c;
+        chk(kr_normest(ctx(), matrix_of(prhs[0]), mxGetScalar(prhs[1]), &e, &c));
+        plhs[0] = scalar(e);
+        if (nlhs > 1) plhs[1] = scalar((double)c);
+    } else if (!strcmp(op, "normAm")) {                            /* [c,mv] = (A,m) */
+        double c; int64_t mv;
+        chk(kr_normAm(ctx(), matrix_of(prhs[0]), 1.0, (int64_t)mxGetScalar(prhs[1]), &c, &mv));
+        plhs[0] = scalar(c);
+        if (nlhs > 1) plhs[1] = scalar((double)mv);
+    } else if (!strcmp(op, "select_taylor_degree")) {              /* [M,mv,alpha,unA] = (A,ncols,m_max,p_max,shift,force) */
+        int64_t mmax = (int64_t)mxGetScalar(prhs[2]), pmax = (int64_t)mxGetScalar(prhs[3]), mv; int unA;
+        plhs[0] = mxCreateDoubleMatrix((mwSize)mmax, (mwSize)(pmax - 1), mxREAL);
+        { mxArray* al = mxCreateDoubleMatrix((mwSize)(pmax - 1), 1, mxREAL);
+          chk(kr_select_taylor_degree(ctx(), matrix_of(prhs[0]), 1.0, (int64_t)mxGetScalar(prhs[1]), mmax, pmax,
+                                      (int)mxGetScalar(prhs[4]), (int)mxGetScalar(prhs[5]), mxGetPr(plhs[0]), &mv, mxGetPr(al), &unA));
+          if (nlhs > 1) plhs[1] = scalar((double)mv);
+          if (nlhs > 2) plhs[2] = al; else mxDestroyArray(al);
+          if (nlhs > 3) plhs[3] = scalar((double)unA); }
+    } else if (!strcmp(op, "expmv")) {                             /* [f,s,m,mv,mvd,unA] = (t,A,b,M,shift,full_term) */
+        kr_matrix* M = matrix_of(prhs[1]);
+        mwSize n = mxGetM(prhs[2]), q = mxGetN(prhs[2]);
+        int hasM = !mxIsEmpty(prhs[3]);
+        int64_t s, m, mv, mvd; int unA;
+        plhs[0] = mxCreateDoubleMatrix(n, q, mxREAL);
+        chk(kr_expmv(ctx(), M, mxGetScalar(prhs[0]), (int64_t)q, mxGetPr(prhs[2]), (int64_t)n,
+                     hasM ? mxGetPr(prhs[3]) : NULL, hasM ? (int64_t)mxGetM(prhs[3]) : 0, hasM ? (int64_t)mxGetN(prhs[3]) : 0,
+                     (int)mxGetScalar(prhs[4]), (int)mxGetScalar(prhs[5]), mxGetPr(plhs[0]), (int64_t)n, &s, &m, &mv, &mvd, &unA));
+        if (nlhs > 1) plhs[1] = scalar((double)s);
+        if (nlhs > 2) plhs[2] = scalar((double)m);
+        if (nlhs > 3) plhs[3] = scalar((double)mv);
+        if (nlhs > 4) plhs[4] = scalar((double)mvd);
+        if (nlhs > 5) plhs[5] = scalar((double)unA);
+    } else if (!strcmp(op, "mc_trace")) {                          /* [tr,res,it] = (A,op,tol,maxit,probes) */
+        double tr, res; int64_t it;
+        chk(kr_mc_trace(ctx(), matrix_of(prhs[0]), (int)mxGetScalar(prhs[1]), mxGetScalar(prhs[2]),
+                        (int64_t)mxGetScalar(prhs[3]), mxGetPr(prhs[4]), &tr, &res, &it));
+        plhs[0] = scalar(tr);
+        if (nlhs > 1) plhs[1] = scalar(res);
+        if (nlhs > 2) plhs[2] = scalar((double)it);
+    } else if (!strcmp(op, "krylov_start") || !strcmp(op, "krylov_extend") || !strcmp(op, "krylov_free")) {
+        /* state handle travels as a uint64 scalar inside params.handle:
+         * [V,H,K,last,lucky,handle] = kr_mex('krylov_start', A, b, arnoldi) / ('krylov_extend', handle) */
+        kr_krylov* st = NULL; int lucky = 0; int64_t d[5];
+        if (!strcmp(op, "krylov_free")) { kr_krylov_destroy(*(kr_krylov**)mxGetData(prhs[0])); return; }
+        if (!strcmp(op, "krylov_start")) {
+            chk(kr_krylov_start(ctx(), matrix_of(prhs[0]), (int)mxGetScalar(prhs[2]), (int64_t)mxGetN(prhs[1]),
+                                mxGetPr(prhs[1]), (int64_t)mxGetM(prhs[1]), &st, &lucky));
+        } else {
+            st = *(kr_krylov**)mxGetData(prhs[0]);
+            chk(kr_krylov_extend(st, &lucky));
+        }
+        chk(kr_krylov_dims(st, d));
+        /* rows of V = rows of b (start) - the wrapper passes n explicitly on extend as prhs[1] */
+        {
+            mwSize n = (mwSize)(strcmp(op, "krylov_start") ? mxGetScalar(prhs[1]) : mxGetM(prhs[1]));
+            plhs[0] = mxCreateDoubleMatrix(n, (mwSize)d[4], mxREAL);
+            plhs[1] = mxCreateDoubleMatrix((mwSize)d[2], (mwSize)d[3], mxREAL);
+            plhs[2] = mxCreateDoubleMatrix((mwSize)d[2], (mwSize)d[3], mxREAL);
+            plhs[3] = mxCreateDoubleMatrix(n, (mwSize)d[0], mxREAL);
+            chk(kr_krylov_get(st, mxGetPr(plhs[0]), (int64_t)n, mxGetPr(plhs[1]), d[2], mxGetPr(plhs[2]), d[2],
+                              mxGetPr(plhs[3]), (int64_t)n));
+            plhs[4] = mxCreateLogicalScalar(lucky != 0);
+            plhs[5] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+            *(kr_krylov**)mxGetData(plhs[5]) = st;
+        }
+    } else {
+        mexErrMsgIdAndTxt("krylov_b200:op", "unknown op '%s'", op);
+    }
+}
