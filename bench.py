@@ -54,18 +54,36 @@ def config_dict(world):
 
 
 # ------------------------------------------------------------------------------- CPU arms
+_CPU_A = None      # set before forking so the workers inherit the matrix instead of unpickling it
+
+
 def _cpu_worker(args):
-    A, Z, m = args
+    col_offset, cols, m = args
     import oracle
-    return oracle.slq_trace(A, Z, m, "exp")[0]
+    Z = _rademacher(_CPU_A.shape[0], cols, PROBE_SEED, col_offset)
+    return oracle.slq_trace(_CPU_A, Z, m, "exp")[0]
+
+
+def _rademacher(n, k, seed, col_offset):
+    """Same counter-based +-1 stream as the device (splitmix64 of seed ^ (col << 32 | row)); restated here
+    so the CPU arms do not touch the engine package."""
+    i = np.arange(n, dtype=np.uint64)[:, None]
+    c = (np.arange(k, dtype=np.uint64) + np.uint64(col_offset))[None, :]
+    x = np.uint64(seed) ^ ((c << np.uint64(32)) | i)
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return np.where((x >> np.uint64(63)) == 1, -1.0, 1.0)
 
 
 def cpu_slq_rate(A, cols_per_proc, procs, m):
     """matvecs/s of the oracle's SLQ on `procs` host processes (each: cols_per_proc probes)."""
-    from krylov_robustness_b200.engine import rademacher_host
     import multiprocessing as mp
-    n = A.shape[0]
-    jobs = [(A, rademacher_host(n, cols_per_proc, PROBE_SEED, col_offset=p * cols_per_proc), m) for p in range(procs)]
+    global _CPU_A
+    _CPU_A = A
+    jobs = [(p * cols_per_proc, cols_per_proc, m) for p in range(procs)]
     t0 = time.perf_counter()
     if procs == 1:
         _cpu_worker(jobs[0])

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkrylov_b200.so")
+LIB_PATH = os.environ.get("KR_B200_LIB", os.path.join(_HERE, "libkrylov_b200.so"))   # override: tuning builds
 
 c_i64 = C.c_int64
 c_dp = C.POINTER(C.c_double)

@@ -5,6 +5,6 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
     -Xcompiler -fPIC,-Wall,-Wno-unused-function -shared \
-    ${KR_PTXAS_V:+-Xptxas -v} \
-    -o ../libkrylov_b200.so api.cu \
+    ${KR_PTXAS_V:+-Xptxas -v} ${KR_EXTRA_FLAGS} \
+    -o ${KR_OUT:-../libkrylov_b200.so} api.cu \
     -lcublas -lcusolver -Xlinker -rpath=/usr/local/cuda/lib64

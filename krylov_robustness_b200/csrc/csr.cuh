@@ -22,7 +22,7 @@ namespace kr {
 struct RowTile {
     int start;      // offset into row_order
     int count;      // rows in this tile
-    int lanes_log2; // lanes per row: 2 (4 lanes) .. 5 (32 lanes)
+    int lanes_log2; // log2 of the nonzero slots per row (0..3); 6 = one long row for the whole CTA
     int pad;
 };
 
@@ -44,8 +44,14 @@ struct CsrDevView {
     const RowTile* __restrict__ tiles;
 };
 
-constexpr int SPMM_CAP = 4096;        // nonzeros staged in shared memory per multi-row tile
-constexpr int SPMM_MAX_ROWS = 1024;   // rows per tile
+#ifndef KR_SPMM_CAP
+#define KR_SPMM_CAP 4096
+#endif
+#ifndef KR_SPMM_MAX_ROWS
+#define KR_SPMM_MAX_ROWS 1024
+#endif
+constexpr int SPMM_CAP = KR_SPMM_CAP;             // nonzeros staged in shared memory per multi-row tile
+constexpr int SPMM_MAX_ROWS = KR_SPMM_MAX_ROWS;   // rows per tile
 constexpr int SPMM_LONG_ROW = 1024;   // rows at least this long are processed by a whole CTA
 
 struct CsrDev {
@@ -156,7 +162,7 @@ inline void upload_csr(kr_ctx* ctx, const CsrHost& H, CsrDev& D) {
     }
     // ---- tiles: runs of one lane class, nonzeros <= SPMM_CAP, rows <= SPMM_MAX_ROWS; long rows alone
     auto lane_class = [](int len) {
-        return len >= SPMM_LONG_ROW ? 6 : len >= 256 ? 5 : len >= 64 ? 4 : len >= 16 ? 3 : 2;
+        return len >= SPMM_LONG_ROW ? 6 : len >= 256 ? 3 : len >= 64 ? 2 : len >= 16 ? 1 : 0;
     };
     std::vector<RowTile> tiles;
     int64_t i = 0;

@@ -107,7 +107,7 @@ constexpr int COL_ROWS_PER_CTA = 2048;   // rows of one panel handled by one CTA
 
 inline int col_row_blocks(int64_t n) { return (int)ceil_div(n, COL_ROWS_PER_CTA); }
 
-// deterministic CTA reduction of NV values per (threadIdx.x & 3) class -> lanes 0..3 of warp 0
+// deterministic CTA reduction of NV values per (threadIdx.x % LPT) class -> lanes 0..LPT-1 of warp 0
 template <int NV>
 __device__ __forceinline__ void col_cta_reduce(double (&v)[NV], double* smem) {
     cta_reduce_by_sub<NV>(v, smem);      // same 8-warp shape as the SpMM CTA
@@ -116,19 +116,19 @@ __device__ __forceinline__ void col_cta_reduce(double (&v)[NV], double* smem) {
 // partial[rb][col] = sum over the CTA's rows of X(r,col)^2.  grid = (row_blocks, panels)
 __global__ void __launch_bounds__(COL_THREADS)
 colnorm2_kernel(const double* __restrict__ X, int64_t n, double* __restrict__ partial, int total_cols) {
-    __shared__ double smem[SPMM_WARPS * 4 * 2];
-    const int q = blockIdx.y, sub = threadIdx.x & 3;
+    __shared__ double smem[SPMM_WARPS * LPT * 2];
+    const int q = blockIdx.y, sub = threadIdx.x % LPT;
     const double* Xp = X + (int64_t)q * n * PW;
     const int64_t r0 = (int64_t)blockIdx.x * COL_ROWS_PER_CTA;
     const int64_t r1 = min(n, r0 + COL_ROWS_PER_CTA);
     double acc[2] = {0.0, 0.0};
-    for (int64_t r = r0 + (threadIdx.x >> 2); r < r1; r += COL_THREADS / 4) {
+    for (int64_t r = r0 + (threadIdx.x / LPT); r < r1; r += COL_THREADS / LPT) {
         double2 x = *reinterpret_cast<const double2*>(Xp + r * PW + sub * 2);
         acc[0] += x.x * x.x;
         acc[1] += x.y * x.y;
     }
     col_cta_reduce<2>(acc, smem);
-    if (threadIdx.x < 4) {
+    if (threadIdx.x < LPT) {
         double* o = partial + (int64_t)blockIdx.x * total_cols + q * PW + threadIdx.x * 2;
         o[0] = acc[0];
         o[1] = acc[1];
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(COL_THREADS)
 combine3_norm_kernel(const double* __restrict__ Y, const double* __restrict__ U1,
                      const double* U0, double* W, int64_t n, const double* __restrict__ coef,
                      int total_cols, double* __restrict__ partial) {
-    __shared__ double smem[SPMM_WARPS * 4 * 2];
-    const int q = blockIdx.y, sub = threadIdx.x & 3;
+    __shared__ double smem[SPMM_WARPS * LPT * 2];
+    const int q = blockIdx.y, sub = threadIdx.x % LPT;
     const int64_t po = (int64_t)q * n * PW;
     const int col = q * PW + sub * 2;
     const double c0x = coef[col], c0y = coef[col + 1];
@@ -151,7 +151,7 @@ combine3_norm_kernel(const double* __restrict__ Y, const double* __restrict__ U1
     const int64_t r0 = (int64_t)blockIdx.x * COL_ROWS_PER_CTA;
     const int64_t r1 = min(n, r0 + COL_ROWS_PER_CTA);
     double acc[2] = {0.0, 0.0};
-    for (int64_t r = r0 + (threadIdx.x >> 2); r < r1; r += COL_THREADS / 4) {
+    for (int64_t r = r0 + (threadIdx.x / LPT); r < r1; r += COL_THREADS / LPT) {
         const int64_t o = po + r * PW + sub * 2;
         double2 y = __ldcs(reinterpret_cast<const double2*>(Y + o));
         double2 u1 = *reinterpret_cast<const double2*>(U1 + o);
@@ -164,7 +164,7 @@ combine3_norm_kernel(const double* __restrict__ Y, const double* __restrict__ U1
         acc[1] += w.y * w.y;
     }
     col_cta_reduce<2>(acc, smem);
-    if (threadIdx.x < 4) {
+    if (threadIdx.x < LPT) {
         double* o = partial + (int64_t)blockIdx.x * total_cols + q * PW + threadIdx.x * 2;
         o[0] = acc[0];
         o[1] = acc[1];

@@ -20,15 +20,15 @@ struct PtrChunk { const double* v[MD_CHUNK]; };
 // partial[(rb*nl + l)*tc + col] = sum_rows V_l(r,col) * W(r,col),  l < nl <= 8
 __global__ void __launch_bounds__(COL_THREADS)
 multi_dot_kernel(PtrChunk V, int nl, const double* __restrict__ W, int64_t n, int tc, double* __restrict__ partial) {
-    __shared__ double smem[SPMM_WARPS * 4 * 2];
-    const int q = blockIdx.y, sub = threadIdx.x & 3;
+    __shared__ double smem[SPMM_WARPS * LPT * 2];
+    const int q = blockIdx.y, sub = threadIdx.x % LPT;
     const int64_t po = (int64_t)q * n * PW;
     const int64_t r0 = (int64_t)blockIdx.x * COL_ROWS_PER_CTA;
     const int64_t r1 = min(n, r0 + COL_ROWS_PER_CTA);
     double acc[MD_CHUNK][2];
 #pragma unroll
     for (int l = 0; l < MD_CHUNK; ++l) acc[l][0] = acc[l][1] = 0.0;
-    for (int64_t r = r0 + (threadIdx.x >> 2); r < r1; r += COL_THREADS / 4) {
+    for (int64_t r = r0 + (threadIdx.x / LPT); r < r1; r += COL_THREADS / LPT) {
         const int64_t o = po + r * PW + sub * 2;
         double2 w = *reinterpret_cast<const double2*>(W + o);
 #pragma unroll
@@ -44,7 +44,7 @@ multi_dot_kernel(PtrChunk V, int nl, const double* __restrict__ W, int64_t n, in
         if (l < nl) {                        // uniform across the CTA
             double a[2] = {acc[l][0], acc[l][1]};
             cta_reduce_by_sub<2>(a, smem);
-            if (threadIdx.x < 4) {
+            if (threadIdx.x < LPT) {
                 double* o = partial + ((int64_t)blockIdx.x * nl + l) * tc + q * PW + threadIdx.x * 2;
                 o[0] = a[0];
                 o[1] = a[1];
@@ -57,7 +57,7 @@ multi_dot_kernel(PtrChunk V, int nl, const double* __restrict__ W, int64_t n, in
 // W(r,col) -= sum_l h[l][col] * V_l(r,col)
 __global__ void __launch_bounds__(COL_THREADS)
 multi_axpy_kernel(PtrChunk V, int nl, double* __restrict__ W, int64_t n, int tc, const double* __restrict__ h) {
-    const int q = blockIdx.y, sub = threadIdx.x & 3;
+    const int q = blockIdx.y, sub = threadIdx.x % LPT;
     const int64_t po = (int64_t)q * n * PW;
     const int col = q * PW + sub * 2;
     double hx[MD_CHUNK], hy[MD_CHUNK];
@@ -68,7 +68,7 @@ multi_axpy_kernel(PtrChunk V, int nl, double* __restrict__ W, int64_t n, int tc,
     }
     const int64_t r0 = (int64_t)blockIdx.x * COL_ROWS_PER_CTA;
     const int64_t r1 = min(n, r0 + COL_ROWS_PER_CTA);
-    for (int64_t r = r0 + (threadIdx.x >> 2); r < r1; r += COL_THREADS / 4) {
+    for (int64_t r = r0 + (threadIdx.x / LPT); r < r1; r += COL_THREADS / LPT) {
         const int64_t o = po + r * PW + sub * 2;
         double2 w = *reinterpret_cast<const double2*>(W + o);
 #pragma unroll
@@ -85,13 +85,13 @@ multi_axpy_kernel(PtrChunk V, int nl, double* __restrict__ W, int64_t n, int tc,
 // W(r,col) *= s[col]
 __global__ void __launch_bounds__(COL_THREADS)
 colscale_kernel(double* __restrict__ W, int64_t n, int tc, const double* __restrict__ s) {
-    const int q = blockIdx.y, sub = threadIdx.x & 3;
+    const int q = blockIdx.y, sub = threadIdx.x % LPT;
     const int64_t po = (int64_t)q * n * PW;
     const int col = q * PW + sub * 2;
     const double sx = s[col], sy = s[col + 1];
     const int64_t r0 = (int64_t)blockIdx.x * COL_ROWS_PER_CTA;
     const int64_t r1 = min(n, r0 + COL_ROWS_PER_CTA);
-    for (int64_t r = r0 + (threadIdx.x >> 2); r < r1; r += COL_THREADS / 4) {
+    for (int64_t r = r0 + (threadIdx.x / LPT); r < r1; r += COL_THREADS / LPT) {
         const int64_t o = po + r * PW + sub * 2;
         double2 w = *reinterpret_cast<const double2*>(W + o);
         w.x *= sx;

@@ -35,11 +35,11 @@ __global__ void __launch_bounds__(COL_THREADS)
 pair_update_kernel(double* __restrict__ Y, const double* __restrict__ P, const double* __restrict__ C,
                    int64_t n, const double* __restrict__ coef, int ncand, double* __restrict__ partial) {
     constexpr int NV = MODE == 0 ? 8 : 4;
-    __shared__ double smem[SPMM_WARPS * 4 * NV];
-    __shared__ double cf[4][12];
-    const int q = blockIdx.y, sub = threadIdx.x & 3;
-    if (threadIdx.x < 48) {
-        int cand = q * 4 + threadIdx.x / 12;
+    __shared__ double smem[SPMM_WARPS * LPT * NV];
+    __shared__ double cf[LPT][12];
+    const int q = blockIdx.y, sub = threadIdx.x % LPT;
+    if (threadIdx.x < LPT * 12) {
+        int cand = q * LPT + threadIdx.x / 12;
         cf[threadIdx.x / 12][threadIdx.x % 12] = cand < ncand ? coef[(int64_t)cand * 12 + threadIdx.x % 12] : 0.0;
     }
     __syncthreads();
@@ -50,7 +50,7 @@ pair_update_kernel(double* __restrict__ Y, const double* __restrict__ P, const d
     double acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-    for (int64_t r = r0 + (threadIdx.x >> 2); r < r1; r += COL_THREADS / 4) {
+    for (int64_t r = r0 + (threadIdx.x / LPT); r < r1; r += COL_THREADS / LPT) {
         const int64_t o = po + r * PW + sub * 2;
         double2 y = *reinterpret_cast<const double2*>(Y + o);
         double2 c = *reinterpret_cast<const double2*>(C + o);
@@ -68,9 +68,9 @@ pair_update_kernel(double* __restrict__ Y, const double* __restrict__ P, const d
         }
     }
     cta_reduce_by_sub<NV>(acc, smem);
-    if (threadIdx.x < 4) {
-        int cand = q * 4 + threadIdx.x;
-        double* o = partial + ((int64_t)blockIdx.x * (gridDim.y * 4) + cand) * NV;
+    if (threadIdx.x < LPT) {
+        int cand = q * LPT + threadIdx.x;
+        double* o = partial + ((int64_t)blockIdx.x * (gridDim.y * LPT) + cand) * NV;
 #pragma unroll
         for (int i = 0; i < NV; ++i) o[i] = acc[i];
     }
@@ -308,7 +308,7 @@ inline void pairs_run_chunk(kr_ctx* ctx, const kr_matrix* M, const int64_t* E_de
     const int cols = 2 * ncand;
     PanelBuf B0(ctx, n, cols), B1(ctx, n, cols), B2(ctx, n, cols);
     const int panels = B0.panels;
-    const int ncp = panels * 4;                       // candidates padded to whole panels
+    const int ncp = panels * LPT;                     // candidates padded to whole panels
     B0.buf.zero();
     B1.buf.zero();
     B2.buf.zero();

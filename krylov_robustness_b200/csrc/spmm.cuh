@@ -19,10 +19,16 @@
 
 namespace kr {
 
-constexpr int PW = 8;              // panel width (columns)
+#ifndef KR_PW
+#define KR_PW 16
+#endif
+constexpr int PW = KR_PW;          // panel width (columns): 8 (64 B row-tiles) or 16 (128 B row-tiles)
+constexpr int LPT = PW / 2;        // lanes per row-tile (one double2 per lane)
+static_assert(PW == 8 || PW == 16, "panel width must be 8 or 16");
 constexpr int SPMM_THREADS = 256;  // 8 warps
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
-constexpr int SPMM_DEFAULT_UNROLL = 8;  // independent gathers per lane before the first FMA
+constexpr int SPMM_DEFAULT_UNROLL = 8;
+constexpr int SPMM_DEFAULT_PANELS_PER_CTA = 1;  // consecutive panels walked with one staging of the tile's indices  // independent gathers per lane before the first FMA
 
 struct PanelBlock {                // non-owning view of a panel-major block
     double* p;
@@ -33,7 +39,15 @@ struct PanelBlock {                // non-owning view of a panel-major block
 };
 
 __device__ __forceinline__ double2 ld_x(const double* p) {      // gathered operand: keep in L1/L2
+#if defined(KR_X_LOAD_CG)
+    return __ldcg(reinterpret_cast<const double2*>(p));          // tuning build: L2 only, no L1 allocation
+#elif defined(KR_X_LOAD_NOALLOC)
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+#else
     return __ldg(reinterpret_cast<const double2*>(p));
+#endif
 }
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
@@ -46,29 +60,28 @@ __device__ __forceinline__ double2 shfl_xor2(double2 v, int off) {
     return v;
 }
 
-// Sum NV per-thread values over all threads of the CTA that share (lane & 3), deterministically,
-// and hand the totals to lanes 0..3 of warp 0.  smem: SPMM_WARPS * 4 * NV doubles.
+// Sum NV per-thread values over all threads of the CTA that share (lane % LPT), deterministically,
+// and hand the totals to lanes 0..LPT-1 of warp 0.  smem: SPMM_WARPS * LPT * NV doubles.
 template <int NV>
 __device__ __forceinline__ void cta_reduce_by_sub(double (&v)[NV], double* smem) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         double x = v[i];
-        x += __shfl_xor_sync(0xffffffffu, x, 4);
-        x += __shfl_xor_sync(0xffffffffu, x, 8);
-        x += __shfl_xor_sync(0xffffffffu, x, 16);
+#pragma unroll
+        for (int off = LPT; off < 32; off <<= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
         v[i] = x;
     }
-    if (lane < 4) {
+    if (lane < LPT) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) smem[(warp * 4 + lane) * NV + i] = v[i];
+        for (int i = 0; i < NV; ++i) smem[(warp * LPT + lane) * NV + i] = v[i];
     }
     __syncthreads();
-    if (warp == 0 && lane < 4) {
+    if (warp == 0 && lane < LPT) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             double s = 0.0;
-            for (int w = 0; w < SPMM_WARPS; ++w) s += smem[(w * 4 + lane) * NV + i];
+            for (int w = 0; w < SPMM_WARPS; ++w) s += smem[(w * LPT + lane) * NV + i];
             v[i] = s;
         }
     }
@@ -126,7 +139,7 @@ struct EpiDot {
     }
     __device__ __forceinline__ void finish(int tile, int panel, double* smem) {
         cta_reduce_by_sub<2>(acc, smem);
-        if (threadIdx.x < 4) {
+        if (threadIdx.x < LPT) {
             double* o = partial + (int64_t)tile * total_cols + panel * PW + threadIdx.x * 2;
             o[0] = acc[0];
             o[1] = acc[1];
@@ -141,7 +154,7 @@ struct EpiGram2 {
     const double* __restrict__ P;  // previous block panel base (may be nullptr at step 1)
     const double* __restrict__ C;  // current block panel base (== X)
     double* __restrict__ partial;  // [ntiles][ncand_padded][8]
-    int ncand;                     // panels * 4
+    int ncand;                     // panels * LPT
     double acc[8];
     __device__ __forceinline__ void init(int q, int64_t stride) {
         Y += q * stride;
@@ -170,8 +183,8 @@ struct EpiGram2 {
     }
     __device__ __forceinline__ void finish(int tile, int panel, double* smem) {
         cta_reduce_by_sub<8>(acc, smem);
-        if (threadIdx.x < 4) {
-            double* o = partial + ((int64_t)tile * ncand + panel * 4 + threadIdx.x) * 8;
+        if (threadIdx.x < LPT) {
+            double* o = partial + ((int64_t)tile * ncand + panel * LPT + threadIdx.x) * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = acc[i];
         }
@@ -218,10 +231,11 @@ struct EpiTaylor {
         double ab = fabs(y.x) + fabs(y.y), af = fabs(f.x) + fabs(f.y);
         // the four slot-0 lanes of a row hold its 8 columns: fold over sub.  m = ballot of the
         // lanes that entered the epilogue (the four subs of a row always enter together).
-        ab += __shfl_xor_sync(m, ab, 1);
-        af += __shfl_xor_sync(m, af, 1);
-        ab += __shfl_xor_sync(m, ab, 2);
-        af += __shfl_xor_sync(m, af, 2);
+#pragma unroll
+        for (int off = 1; off < LPT; off <<= 1) {
+            ab += __shfl_xor_sync(m, ab, off);
+            af += __shfl_xor_sync(m, af, off);
+        }
         if (sub == 0) {
             rab[r] = ab;
             raf[r] = af;
@@ -246,22 +260,25 @@ __device__ __forceinline__ double2 gather_accumulate(int p_first, int p_end, int
     double2 acc0 = make_double2(0.0, 0.0), acc1 = acc0;
     for (int p = p_first; p < p_end; p += U * stride) {
         double2 x[U];
+        double v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int q = p + u * stride;
-            const int c = scol[q < p_end ? q : p];
-            x[u] = ld_x(xs + (int64_t)c * PW);
+            x[u] = make_double2(0.0, 0.0);
+            v[u] = 1.0;
+            if (q < p_end) {                                     // predicated: no index / X traffic past the row end
+                x[u] = ld_x(xs + (int64_t)scol[q] * PW);
+                if (HAS_VAL) v[u] = sval[q];
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int q = p + u * stride;
-            const double v = q < p_end ? (HAS_VAL ? sval[q] : 1.0) : 0.0;
             if (u & 1) {
-                acc1.x = fma(v, x[u].x, acc1.x);
-                acc1.y = fma(v, x[u].y, acc1.y);
+                acc1.x = fma(v[u], x[u].x, acc1.x);
+                acc1.y = fma(v[u], x[u].y, acc1.y);
             } else {
-                acc0.x = fma(v, x[u].x, acc0.x);
-                acc0.y = fma(v, x[u].y, acc0.y);
+                acc0.x = fma(v[u], x[u].x, acc0.x);
+                acc0.y = fma(v[u], x[u].y, acc0.y);
             }
         }
     }
@@ -275,11 +292,11 @@ template <int L, bool HAS_VAL, int U, class Epi>
 __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict__ srp, const int* __restrict__ srid,
                                           const int* __restrict__ scol, const double* __restrict__ sval,
                                           const double* __restrict__ Xp, double uval, Epi& epi) {
-    constexpr int S = L / 4;            // nonzero slots per row
+    constexpr int S = L / LPT;          // nonzero slots per row
     constexpr int RPW = 32 / L;         // rows per warp per pass
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane & 3;
-    const int slot = (lane % L) >> 2;
+    const int sub = lane % LPT;
+    const int slot = (lane % L) / LPT;
     const int rlocal = lane / L;
     const double* xs = Xp + sub * 2;
     for (int base = warp * RPW; base < t.count; base += SPMM_WARPS * RPW) {
@@ -295,7 +312,7 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict
         if (emit) epi.pre(row, sub);    // row-local operands: issue their loads before the gathers
         double2 acc = gather_accumulate<HAS_VAL, U>(p0 + slot, p1, S, scol, sval, xs);
 #pragma unroll
-        for (int off = 4; off < L; off <<= 1) {
+        for (int off = LPT; off < L; off <<= 1) {
             double2 o = shfl_xor2(acc, off);
             acc.x += o.x;
             acc.y += o.y;
@@ -309,68 +326,78 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict
     }
 }
 
-// grid = (ntiles, panels); X panel q at X + q*n*8.  `done` (may be null): skip everything if set.
+// grid = (ntiles, ceil(panels/ppc)); X panel q at X + q*n*8.  `done` (may be null): skip everything if set.
 template <class Epi, bool HAS_VAL, int U>
 __global__ void __launch_bounds__(SPMM_THREADS, 4)
 spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t panel_stride,
-            const int* __restrict__ done) {
+            const int* __restrict__ done, int panels, int ppc) {
     if (done && *done) return;
-    __shared__ double red[SPMM_WARPS * 4 * 8];
+    __shared__ double red[SPMM_WARPS * LPT * 8];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     int* scol = reinterpret_cast<int*>(dyn_smem);
     int* srp = scol + SPMM_CAP;
     int* srid = srp + SPMM_MAX_ROWS + 1;
     double* sval = reinterpret_cast<double*>(dyn_smem + SPMM_SMEM_PATTERN);
-    const int tile = blockIdx.x, panel = blockIdx.y;
+    const int tile = blockIdx.x;
     const RowTile t = A.tiles[tile];
-    Epi epi = epi_proto;
-    epi.init(panel, panel_stride);
-    const double* Xp = X + (int64_t)panel * panel_stride;
     const int pb = __ldg(A.row_ptr + t.start);
     const int nz = __ldg(A.row_ptr + t.start + t.count) - pb;
-    if (t.lanes_log2 == 6) {
-        // one long row, whole CTA: stage the indices chunk by chunk, 64 nonzero slots stride each chunk
-        const int sub = threadIdx.x & 3, slot = threadIdx.x >> 2;
-        const int row = __ldg(A.row_order + t.start);
-        const bool emit = threadIdx.x < 4;
-        if (emit) epi.pre(row, sub);
-        double v[2] = {0.0, 0.0};
-        for (int c0 = 0; c0 < nz; c0 += SPMM_CAP) {
-            const int cn = min(SPMM_CAP, nz - c0);
-            __syncthreads();
-            for (int p = threadIdx.x; p < cn; p += SPMM_THREADS) scol[p] = ld_stream(A.col + pb + c0 + p);
-            if (HAS_VAL)
-                for (int p = threadIdx.x; p < cn; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + c0 + p);
-            __syncthreads();
-            double2 a = gather_accumulate<HAS_VAL, U>(slot, cn, SPMM_THREADS / 4, scol, sval, Xp + sub * 2);
-            v[0] += a.x;
-            v[1] += a.y;
-        }
-        cta_reduce_by_sub<2>(v, red);                  // totals in threads 0..3
-        double2 acc = make_double2(v[0], v[1]);
-        if (!HAS_VAL) {
-            acc.x *= A.uval;
-            acc.y *= A.uval;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, emit);
-        if (emit) epi.row(row, sub, acc, m);
-        __syncthreads();                               // red[] is reused by epi.finish
-    } else {
-        // stage the tile's row pointers, row numbers and column indices (coalesced streams)
+    const bool long_row = t.lanes_log2 == 6;   // class 6: one row, whole CTA
+    if (!long_row) {
+        // stage the tile's row pointers, row numbers and column indices (coalesced streams) ONCE; the
+        // CTA then walks `ppc` consecutive panels with them
         for (int i = threadIdx.x; i <= t.count; i += SPMM_THREADS) srp[i] = __ldg(A.row_ptr + t.start + i) - pb;
         for (int i = threadIdx.x; i < t.count; i += SPMM_THREADS) srid[i] = __ldg(A.row_order + t.start + i);
         for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) scol[p] = ld_stream(A.col + pb + p);
         if (HAS_VAL)
             for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + p);
         __syncthreads();
-        switch (t.lanes_log2) {
-            case 2: spmm_tile<4, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
-            case 3: spmm_tile<8, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
-            case 4: spmm_tile<16, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
-            default: spmm_tile<32, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
-        }
     }
-    epi.finish(tile, panel, red);
+    const int panel_end = min(panels, (int)(blockIdx.y + 1) * ppc);
+    for (int panel = blockIdx.y * ppc; panel < panel_end; ++panel) {
+        Epi epi = epi_proto;
+        epi.init(panel, panel_stride);
+        const double* Xp = X + (int64_t)panel * panel_stride;
+        if (long_row) {
+            // one long row, whole CTA: stage the indices chunk by chunk, 64 nonzero slots stride each chunk
+            const int sub = threadIdx.x % LPT, slot = threadIdx.x / LPT;
+            const int row = __ldg(A.row_order + t.start);
+            const bool emit = threadIdx.x < LPT;
+            if (emit) epi.pre(row, sub);
+            double v[2] = {0.0, 0.0};
+            for (int c0 = 0; c0 < nz; c0 += SPMM_CAP) {
+                const int cn = min(SPMM_CAP, nz - c0);
+                if (nz > SPMM_CAP || panel == blockIdx.y * ppc) {     // a row that fits stays staged across panels
+                    __syncthreads();
+                    for (int p = threadIdx.x; p < cn; p += SPMM_THREADS) scol[p] = ld_stream(A.col + pb + c0 + p);
+                    if (HAS_VAL)
+                        for (int p = threadIdx.x; p < cn; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + c0 + p);
+                    __syncthreads();
+                }
+                double2 a = gather_accumulate<HAS_VAL, U>(slot, cn, SPMM_THREADS / LPT, scol, sval, Xp + sub * 2);
+                v[0] += a.x;
+                v[1] += a.y;
+            }
+            cta_reduce_by_sub<2>(v, red);                  // totals in threads 0..3
+            double2 acc = make_double2(v[0], v[1]);
+            if (!HAS_VAL) {
+                acc.x *= A.uval;
+                acc.y *= A.uval;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, emit);
+            if (emit) epi.row(row, sub, acc, m);
+            __syncthreads();                               // red[] is reused by epi.finish
+        } else {
+            switch (t.lanes_log2) {          // slots per row = 1 << lanes_log2, lanes per row = LPT << lanes_log2
+                case 0: spmm_tile<LPT, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
+                case 1: spmm_tile<2 * LPT, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
+                case 2: spmm_tile<(4 * LPT > 32 ? 32 : 4 * LPT), HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
+                default: spmm_tile<32, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
+            }
+        }
+        epi.finish(tile, panel, red);
+        __syncthreads();                                   // red[] and the staged indices are reused by the next panel
+    }
 }
 
 // Host-side launcher.  Epilogues carry panel-0 pointers; init() advances them to the CTA's panel.
@@ -384,10 +411,12 @@ inline void launch_spmm(kr_ctx* ctx, const CsrDev& A, const double* X, int panel
         KR_CUDA(cudaEventCreate(&e1));
         KR_CUDA(cudaEventRecord(e0, ctx->stream));
     }
-    dim3 grid((unsigned)A.ntiles, (unsigned)panels);
     static bool attr_set = false;               // one flag per Epi instantiation
     static int variant = 4;
+    static int ppc = SPMM_DEFAULT_PANELS_PER_CTA;
     if (!attr_set) {
+        const char* pe = getenv("KR_SPMM_PPC");      // tuning knob: consecutive panels per CTA
+        if (pe && atoi(pe) >= 1 && atoi(pe) <= 64) ppc = atoi(pe);
         KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_PATTERN));
         KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_VALUED));
         KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_PATTERN));
@@ -397,12 +426,13 @@ inline void launch_spmm(kr_ctx* ctx, const CsrDev& A, const double* X, int panel
         attr_set = true;
     }
     const int64_t ps = (int64_t)A.n * PW;
+    dim3 grid((unsigned)A.ntiles, (unsigned)((panels + ppc - 1) / ppc));
     if (A.pattern_only) {
-        if (variant == 8) spmm_kernel<Epi, false, 8><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done);
-        else spmm_kernel<Epi, false, 4><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done);
+        if (variant == 8) spmm_kernel<Epi, false, 8><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, panels, ppc);
+        else spmm_kernel<Epi, false, 4><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, panels, ppc);
     } else {
-        if (variant == 8) spmm_kernel<Epi, true, 8><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done);
-        else spmm_kernel<Epi, true, 4><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done);
+        if (variant == 8) spmm_kernel<Epi, true, 8><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, panels, ppc);
+        else spmm_kernel<Epi, true, 4><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, panels, ppc);
     }
     check_launch(ctx, "spmm_kernel");
     if (ctx->timing) {
