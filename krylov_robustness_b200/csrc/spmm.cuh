@@ -27,6 +27,10 @@ constexpr int LPT = PW / 2;        // lanes per row-tile (one double2 per lane)
 static_assert(PW == 8 || PW == 16, "panel width must be 8 or 16");
 constexpr int SPMM_THREADS = 256;  // 8 warps
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
+#ifndef KR_SPMM_MIN_CTAS
+#define KR_SPMM_MIN_CTAS 4
+#endif
+constexpr int SPMM_MIN_CTAS = KR_SPMM_MIN_CTAS;   // resident CTAs per SM the register allocation is bounded for
 constexpr int SPMM_DEFAULT_UNROLL = 8;
 constexpr int SPMM_DEFAULT_PANELS_PER_CTA = 1;  // consecutive panels walked with one staging of the tile's indices  // independent gathers per lane before the first FMA
 
@@ -328,9 +332,9 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict
 
 // grid = (ntiles, ceil(panels/ppc)); X panel q at X + q*n*8.  `done` (may be null): skip everything if set.
 template <class Epi, bool HAS_VAL, int U>
-__global__ void __launch_bounds__(SPMM_THREADS, 4)
+__global__ void __launch_bounds__(SPMM_THREADS, SPMM_MIN_CTAS)
 spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t panel_stride,
-            const int* __restrict__ done, int panels, int ppc) {
+            const int* __restrict__ done, int panels, int ppc, int panel0) {
     if (done && *done) return;
     __shared__ double red[SPMM_WARPS * LPT * 8];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -353,8 +357,9 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
             for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + p);
         __syncthreads();
     }
-    const int panel_end = min(panels, (int)(blockIdx.y + 1) * ppc);
-    for (int panel = blockIdx.y * ppc; panel < panel_end; ++panel) {
+    const int panel_first = panel0 + blockIdx.y * ppc;
+    const int panel_end = min(panels, panel_first + ppc);
+    for (int panel = panel_first; panel < panel_end; ++panel) {
         Epi epi = epi_proto;
         epi.init(panel, panel_stride);
         const double* Xp = X + (int64_t)panel * panel_stride;
@@ -367,7 +372,7 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
             double v[2] = {0.0, 0.0};
             for (int c0 = 0; c0 < nz; c0 += SPMM_CAP) {
                 const int cn = min(SPMM_CAP, nz - c0);
-                if (nz > SPMM_CAP || panel == blockIdx.y * ppc) {     // a row that fits stays staged across panels
+                if (nz > SPMM_CAP || panel == panel_first) {     // a row that fits stays staged across panels
                     __syncthreads();
                     for (int p = threadIdx.x; p < cn; p += SPMM_THREADS) scol[p] = ld_stream(A.col + pb + c0 + p);
                     if (HAS_VAL)
@@ -426,14 +431,16 @@ inline void launch_spmm(kr_ctx* ctx, const CsrDev& A, const double* X, int panel
         attr_set = true;
     }
     const int64_t ps = (int64_t)A.n * PW;
-    dim3 grid((unsigned)A.ntiles, (unsigned)((panels + ppc - 1) / ppc));
-    if (A.pattern_only) {
-        if (variant == 8) spmm_kernel<Epi, false, 8><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, panels, ppc);
-        else spmm_kernel<Epi, false, 4><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, panels, ppc);
-    } else {
-        if (variant == 8) spmm_kernel<Epi, true, 8><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, panels, ppc);
-        else spmm_kernel<Epi, true, 4><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, panels, ppc);
-    }
+    auto launch = [&](dim3 grid, int npanels, int panel0) {
+        if (A.pattern_only) {
+            if (variant == 8) spmm_kernel<Epi, false, 8><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0);
+            else spmm_kernel<Epi, false, 4><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0);
+        } else {
+            if (variant == 8) spmm_kernel<Epi, true, 8><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0);
+            else spmm_kernel<Epi, true, 4><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0);
+        }
+    };
+    launch(dim3((unsigned)A.ntiles, (unsigned)((panels + ppc - 1) / ppc)), panels, 0);
     check_launch(ctx, "spmm_kernel");
     if (ctx->timing) {
         KR_CUDA(cudaEventRecord(e1, ctx->stream));
