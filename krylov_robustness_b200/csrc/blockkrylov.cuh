@@ -69,6 +69,94 @@ inline void gemm(kr_ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
     ctx->counters[0] += 1;
 }
 
+// ------------------------------------------------------------------ FP64 tensor-core Gram
+// G = V' W for tall-skinny column-major blocks (V: n x c, W: n x b, b <= 128): the CGS2 / third-pass
+// Gram of functions/lanczos_krylov.m:110-112 and functions/arnoldi_krylov.m:104,120-122 when the block
+// width makes it a real dense contraction.  DMMA m8n8k4 (the only fp64 tensor shape family on sm_100;
+// tcgen05 has no fp64 kind): the A fragment is a 8x4 tile of V' and the B fragment a 4x8 tile of W,
+// both read straight from global memory - 4 consecutive rows of 8 columns = 8 fully used 32-byte
+// sectors per warp load, so no shared-memory staging is needed.  grid = (row chunks, ceil(c/32)); a
+// CTA owns a 32 x b tile of G for its chunk of rows, warp w owns the 8-column tiles w and w+8.
+// Split-K partials land in a fixed layout and are summed in a fixed order (deterministic).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int GRAM_KCH = 4096;     // rows per CTA
+__global__ void __launch_bounds__(256)
+gram_dmma_kernel(const double* __restrict__ V, int64_t ldv, int c, const double* __restrict__ W, int64_t ldw,
+                 int b, int64_t n, double* __restrict__ partial) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kk = lane & 3, idx = lane >> 2;
+    const int m0 = blockIdx.y * 32;
+    const int64_t r0 = (int64_t)blockIdx.x * GRAM_KCH, r1 = min(n, r0 + (int64_t)GRAM_KCH);
+    const int ntiles = (b + 7) >> 3;
+    double acc[4][2][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) acc[mt][s][0] = acc[mt][s][1] = 0.0;
+    const bool has0 = warp < ntiles, has1 = warp + 8 < ntiles;     // warp-uniform
+    if (has0) {
+        for (int64_t k0 = r0; k0 < r1; k0 += 4) {
+            const int64_t row = k0 + kk;
+            const bool rok = row < r1;
+            double a[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                const int col = m0 + mt * 8 + idx;
+                a[mt] = (rok && col < c) ? __ldg(V + row + (int64_t)col * ldv) : 0.0;
+            }
+            {
+                const int col = warp * 8 + idx;
+                const double bb = (rok && col < b) ? __ldg(W + row + (int64_t)col * ldw) : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][0][0], acc[mt][0][1], a[mt], bb);
+            }
+            if (has1) {
+                const int col = (warp + 8) * 8 + idx;
+                const double bb = (rok && col < b) ? __ldg(W + row + (int64_t)col * ldw) : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][1][0], acc[mt][1][1], a[mt], bb);
+            }
+        }
+    }
+    // C fragment: lane holds C[idx][2*kk], C[idx][2*kk+1] of each 8x8 tile; partial is column-major c x b
+    double* out = partial + (int64_t)blockIdx.x * c * b;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int nt = warp + s * 8;
+        if (nt >= ntiles) continue;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int m = m0 + mt * 8 + idx;
+            const int n0 = nt * 8 + 2 * kk;
+            if (m < c) {
+                if (n0 < b) out[m + (int64_t)n0 * c] = acc[mt][s][0];
+                if (n0 + 1 < b) out[m + (int64_t)(n0 + 1) * c] = acc[mt][s][1];
+            }
+        }
+    }
+}
+
+// G (c x b, column-major, device) = V' W.  Falls back to cuBLAS for b > 128.
+inline void gemm(kr_ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                 int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+inline void gram_tn(kr_ctx* ctx, const double* V, int64_t ldv, int64_t c, const double* W, int64_t ldw, int64_t b,
+                    int64_t n, double* G) {
+    if (c == 0 || b == 0) return;
+    if (b > 128) {
+        gemm(ctx, true, false, c, b, n, 1.0, V, ldv, W, ldw, 0.0, G, c);
+        return;
+    }
+    const int chunks = (int)ceil_div(n, GRAM_KCH);
+    DevBuf<double> partial(ctx, (size_t)chunks * c * b);
+    dim3 grid((unsigned)chunks, (unsigned)ceil_div(c, 32));
+    KR_LAUNCH(ctx, gram_dmma_kernel, grid, 256, 0, V, ldv, (int)c, W, ldw, (int)b, n, partial.p);
+    sum_partials(ctx, partial.p, chunks, (int)(c * b), G);
+}
+
 // Y = A * X for column-major device blocks (n x k)
 inline void spmm_cm(kr_ctx* ctx, const kr_matrix* M, const double* X, int64_t k, double* Y) {
     const int64_t n = M->dev.n;
@@ -203,9 +291,9 @@ inline void krylov_step(kr_krylov* st) {
     spmm_cm(ctx, st->A, st->V.col(c - bs), bs, W.p());
     // CGS2 against V (n x c)
     DevBuf<double> dh(ctx, (size_t)c * bs), dh1(ctx, (size_t)c * bs);
-    gemm(ctx, true, false, c, bs, n, 1.0, st->V.p(), n, W.p(), n, 0.0, dh.p, c);
+    gram_tn(ctx, st->V.p(), n, c, W.p(), n, bs, n, dh.p);
     gemm(ctx, false, false, n, bs, c, -1.0, st->V.p(), n, dh.p, c, 1.0, W.p(), n);
-    gemm(ctx, true, false, c, bs, n, 1.0, st->V.p(), n, W.p(), n, 0.0, dh1.p, c);
+    gram_tn(ctx, st->V.p(), n, c, W.p(), n, bs, n, dh1.p);
     gemm(ctx, false, false, n, bs, c, -1.0, st->V.p(), n, dh1.p, c, 1.0, W.p(), n);
     std::vector<double> h = dh.to_host(), h1 = dh1.to_host();
     for (size_t i = 0; i < h.size(); ++i) h[i] += h1[i];
@@ -251,7 +339,7 @@ inline void krylov_step(kr_krylov* st) {
         }
         // third reorthogonalisation (:104-106)
         DevBuf<double> dhh(ctx, (size_t)c * bs);
-        gemm(ctx, true, false, c, bs, n, 1.0, st->V.p(), n, W.p(), n, 0.0, dhh.p, c);
+        gram_tn(ctx, st->V.p(), n, c, W.p(), n, bs, n, dhh.p);
         gemm(ctx, false, false, n, bs, c, -1.0, st->V.p(), n, dhh.p, c, 1.0, W.p(), n);
         std::vector<double> hh = dhh.to_host();
         for (int64_t j = 0; j < bs; ++j)

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(JAC_THREADS)
 pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict__ W, int64_t n, int j) {
     extern __shared__ double dyn[];
     __shared__ JacobiShared sh;
-    __shared__ double Rm[4], Tn[4];
+    __shared__ double Tn[4];
     __shared__ int s_lucky;
     const int h = blockIdx.x;
     if (!st.active[h]) return;
@@ -230,7 +230,6 @@ pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict
             }
         }
         for (int i = 0; i < 4; ++i) {
-            Rm[i] = R[i];
             Tn[i] = T[i];
             Hd[(j - 1) * 4 + i] = st.hc[h * 4 + i];
             Hs[(j - 1) * 4 + i] = st.hp[h * 4 + i];

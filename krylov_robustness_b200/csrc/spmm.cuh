@@ -1,10 +1,11 @@
 // spmm.cuh - CSR x dense-block product over k-wide fp64 blocks, with fused epilogues.
 //
-// Dense blocks on the device are PANEL-MAJOR: the k columns are cut into panels of PW = 8 columns;
-// panel p is a contiguous row-major n x 8 array (64 B per row).  Element (i, c) lives at
-// base[(c / 8) * n * 8 + i * 8 + (c % 8)].  A nonzero A(r, c) therefore gathers ONE 64 B row-tile
-// of X per panel: four lanes x one 128-bit load.  A panel of X (64 MB at n = 1M) is what must stay
-// L2-resident while the CSR arrays stream past it; blockIdx.y (slow index) walks the panels.
+// Dense blocks on the device are PANEL-MAJOR: the k columns are cut into panels of PW columns
+// (PW = 16 by default: 128 B = one cache line per row; PW = 8 also builds and passes the tests);
+// panel p is a contiguous row-major n x PW array.  Element (i, c) lives at
+// base[(c / PW) * n * PW + i * PW + (c % PW)].  A nonzero A(r, c) therefore gathers ONE row-tile of X
+// per panel: LPT = PW/2 lanes x one 128-bit load, one L1 wavefront.  blockIdx.y (slow index) walks the
+// panels so that one panel of X at a time competes for L2 with the streaming CSR arrays.
 //
 // Scheduling: one CTA (8 warps) per RowTile (csr.cuh).  The CTA first streams the tile's row
 // pointers / row numbers / column indices (and values) into shared memory with coalesced loads, so

@@ -101,3 +101,21 @@ def test_full_size_spmm_properties(kr):
     Z = rng.standard_normal((n, 16))
     assert np.abs(M @ (2.0 * X + Z) - (2.0 * Y + (M @ Z))).max() <= 1e-12 * np.abs(Y).max()
     assert abs(np.vdot(X[:, 0], (M @ Z)[:, 0]) - np.vdot(Z[:, 0], Y[:, 0])) <= 1e-9 * np.abs(Y).max() * np.sqrt(n)
+
+
+def test_expmv_rmat_64_columns(kr, O):
+    """Config C4 shape at a size the oracle finishes in seconds: R-MAT graph, 64 right-hand sides,
+    normAm-driven degree selection on the device, scaled so that exp stays in range."""
+    from krylov_robustness_b200.graphs import rmat_graph, spectral_radius_estimate
+    A = rmat_graph(scale=15, nnz=1 << 19, seed=2)
+    lam = spectral_radius_estimate(A, 30)
+    A = (A * (4.0 / lam)).tocsr()
+    n = A.shape[0]
+    b = np.random.default_rng(3).standard_normal((n, 64))
+    f, s, m, mv, mvd, unA = kr.expmv(1, A, b)
+    of, os_, om, omv, omvd, ounA = O.expmv(1, A, b)
+    assert (s, m, mv, mvd, unA) == (os_, om, omv, omvd, ounA)
+    assert np.linalg.norm(f - of) <= 1e-12 * np.linalg.norm(of)
+    # linearity in b (size-independent property)
+    f2 = kr.expmv(1, A, 3.0 * b[:, :5])[0]
+    assert np.linalg.norm(f2 - 3.0 * f[:, :5]) <= 1e-12 * np.linalg.norm(f2)

@@ -81,3 +81,39 @@ def test_slq_matches_oracle(kr, graphs, gname, fun):
     D = kr.Dense(n, 24).upload(Z)
     assert kr.slq_trace(kr.Matrix(A), D, 20, fun) == tr
     assert kr.slq_trace(kr.Matrix(A), D, 20, fun) == tr      # bit-reproducible run to run
+
+
+def test_slq_power_law_64_probes(kr):
+    """A mid-size instance of the bench workload (Chung-Lu power law, hubs + long rows > 1024 nonzeros
+    exercise the CTA-per-row path) against the oracle."""
+    import oracle as O
+    from krylov_robustness_b200.graphs import power_law_graph, spectral_radius_estimate
+    A = power_law_graph(60_000, 2_400_000, 2.1, seed=5)
+    assert np.diff(A.indptr).max() >= 1024
+    A = (A * (1.0 / spectral_radius_estimate(A, 30))).tocsr()
+    n = A.shape[0]
+    Z = kr.rademacher_host(n, 40, 11)
+    tr, vals, al, be = kr.slq_trace(A, Z, 25, "exp", return_details=True)
+    otr, ovals, oal, obe = O.slq_trace(A, Z, 25, "exp")
+    assert abs(tr - otr) <= 1e-10 * abs(otr)
+    assert np.max(np.abs(vals - ovals)) <= 1e-10 * np.max(np.abs(ovals))
+    X = np.random.default_rng(1).standard_normal((n, 21))
+    assert np.abs(kr.Matrix(A) @ X - A @ X).max() <= 1e-13 * np.abs(X).max() * 50
+
+
+def test_empty_and_degenerate_inputs(kr, graphs):
+    A = graphs("oregon_A0")
+    M = kr.Matrix(A)
+    x, it, lucky = kr.trace_fun_update_edges(M, np.zeros((0, 2), dtype=np.int64), -1.0, 1e-3, 100, "exp")
+    assert x.size == 0 and it.size == 0
+    X, it = kr.function_multiple_entries(M, np.zeros((0, 2), dtype=np.int64), "exp", 1e-8, 50)
+    assert X.size == 0 and it == 0
+    with pytest.raises(kr._lib.KrylovB200Error, match="out of range"):
+        kr.trace_fun_update_edges(M, np.array([[1, 700]]), -1.0, 1e-3, 100, "exp")
+    with pytest.raises(ValueError, match="unsupported function handle"):
+        kr.trace_fun_update_edges(M, np.array([[1, 2]]), -1.0, 1e-3, 100, np.tanh)
+    import scipy.sparse as sp
+    Mz = kr.Matrix(sp.csr_matrix((300, 300)))          # all-zero matrix: empty rows everywhere
+    Y = Mz @ np.ones((300, 3))
+    assert np.all(Y == 0)
+    assert Mz.info()["nnz"] == 0
