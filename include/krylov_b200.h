@@ -126,6 +126,12 @@ int  kr_function_multiple_entries(kr_ctx* ctx, const kr_matrix* A, int64_t k, co
 int  kr_fun_and_grad_krylov(kr_ctx* ctx, const kr_matrix* A, int64_t nomega, const double* X,
                             const int64_t* Omega, int fun, int dfun, const double* dfA,
                             double tol, int64_t it, double* f, double* gr);
+/* Hes = hessianfcn_exp(X,A,Omega,tol,it)        functions/hessianfcn_exp.m:1-17
+ * Hes = hessianfcn_fun(X,A,Omega,f,tol,it)      functions/hessianfcn_fun.m:1-17
+ * over functions/multiple_frechet_eval.m:1-211.  Atilde = A + Delta(X,Omega) is assembled by the caller
+ * (hessianfcn_exp.m:4-7); Hes is nomega x nomega column-major; it is capped at 64 Krylov steps. */
+int  kr_frechet_hessian(kr_ctx* ctx, const kr_matrix* Atilde, int64_t nomega, const int64_t* Omega,
+                        int fun, double tol, int64_t it, double* Hes, int64_t* iter);
 /* MATLAB normest(A,tol) as used at functions/fun_and_grad_krylov_fun.m:27 */
 int  kr_normest(kr_ctx* ctx, const kr_matrix* A, double tol, double* est, int64_t* count);
 

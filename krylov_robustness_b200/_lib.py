@@ -53,6 +53,7 @@ PROTOTYPES = {
     "kr_function_multiple_entries": [VP, VP, c_i64, VP, C.c_int, C.c_double, c_i64, VP, c_ip],
     "kr_fun_and_grad_krylov": [VP, VP, c_i64, VP, VP, C.c_int, C.c_int, VP, C.c_double, c_i64,
                                c_dp, VP],
+    "kr_frechet_hessian": [VP, VP, c_i64, VP, C.c_int, C.c_double, c_i64, VP, c_ip],
     "kr_normest": [VP, VP, C.c_double, c_dp, c_ip],
     "kr_normAm": [VP, VP, C.c_double, c_i64, c_dp, c_ip],
     "kr_select_taylor_degree": [VP, VP, C.c_double, c_i64, c_i64, c_i64, C.c_int, C.c_int,

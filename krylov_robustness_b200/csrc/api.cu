@@ -12,6 +12,7 @@
 #include "expmv.cuh"
 #include "blockkrylov.cuh"
 #include "entries.cuh"
+#include "frechet.cuh"
 #include "mctrace.cuh"
 
 using namespace kr;

@@ -199,51 +199,46 @@ __global__ void entries_gather_kernel(const double* const* __restrict__ Vptr, in
     X[p] = s;
 }
 
-struct EntriesResult { std::vector<double> X; int64_t iter = 0; };
+// A family of independent single-vector Arnoldi spaces K_j(A, e_h), one per column of panel-major
+// blocks, advanced together (arnoldi_krylov.m with bs = 1, full CGS2 + third pass).  Shared by
+// function_multiple_entries and multiple_frechet_eval.
+struct ArnoldiBatch {
+    kr_ctx* ctx;
+    const CsrDev* A;
+    int64_t n;
+    int R, it1, panels, tc, rb;
+    std::vector<std::unique_ptr<PanelBuf>> V;      // V[0..j]: basis blocks
+    DevBuf<double> partial, hbuf, inv, Hc;          // Hc[col][step][0..it1]: columns of the Hessenberg matrices
 
-// rows: distinct first indices (1-based, stable order); colof[p]: column of pair p; j2[p]: second index
-inline EntriesResult entries_run(kr_ctx* ctx, const kr_matrix* M, const std::vector<int64_t>& rows,
-                                 const std::vector<int>& colof, const std::vector<int64_t>& j2, int fun,
-                                 double tol, int it) {
-    const CsrDev& A = M->dev;
-    const int64_t n = A.n;
-    const int R = (int)rows.size(), k = (int)colof.size();
-    const int it1 = it + 1;
-    if (it > 110) fail(KR_ERR_UNSUPPORTED, "function_multiple_entries: it > 110 exceeds the shared-memory solver");
-    std::vector<std::unique_ptr<PanelBuf>> V;
-    V.emplace_back(new PanelBuf(ctx, n, R));
-    V[0]->buf.zero();
-    const int panels = V[0]->panels, tc = panels * PW;
-    DevBuf<int64_t> drows(ctx, R), dj2(ctx, k);
-    DevBuf<int> dcolof(ctx, k);
-    drows.upload(rows.data(), R);
-    dj2.upload(j2.data(), k);
-    dcolof.upload(colof.data(), k);
-    KR_LAUNCH(ctx, entries_init_kernel, (int)ceil_div(R, 128), 128, 0, V[0]->p(), n, drows.p, R);
-    const int rb = col_row_blocks(n);
-    DevBuf<double> partial(ctx, (size_t)rb * MD_CHUNK * tc), hbuf(ctx, (size_t)MD_CHUNK * tc), inv(ctx, tc);
-    DevBuf<double> Hc(ctx, (size_t)R * it1 * (it1 + 1)), hist(ctx, (size_t)R * 4 * it1), xfin(ctx, (size_t)R * it1);
-    DevBuf<int> istate(ctx, (size_t)2 * R + 1);
-    Hc.zero(); hist.zero(); xfin.zero(); istate.zero(); inv.zero();
-    int* nfin = istate.p;
-    int* conv = istate.p + R;
-    int* nactive = istate.p + 2 * R;
-    int nact = R;
-    KR_CUDA(cudaMemcpyAsync(nactive, &nact, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    static bool attr_set = false;
-    if (!attr_set) {
-        KR_CUDA(cudaFuncSetAttribute(entries_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_LIMIT));
-        attr_set = true;
+    ArnoldiBatch(kr_ctx* c, const CsrDev& A_, const std::vector<int64_t>& rows, int it) : ctx(c), A(&A_) {
+        n = A_.n;
+        R = (int)rows.size();
+        it1 = it + 1;
+        V.emplace_back(new PanelBuf(ctx, n, R));
+        V[0]->buf.zero();
+        panels = V[0]->panels;
+        tc = panels * PW;
+        rb = col_row_blocks(n);
+        DevBuf<int64_t> drows(ctx, R);
+        drows.upload(rows.data(), R);
+        KR_LAUNCH(ctx, entries_init_kernel, (int)ceil_div(R, 128), 128, 0, V[0]->p(), n, drows.p, R);
+        KR_CUDA(cudaStreamSynchronize(ctx->stream));
+        partial.reset(ctx, (size_t)rb * MD_CHUNK * tc);
+        hbuf.reset(ctx, (size_t)MD_CHUNK * tc);
+        inv.reset(ctx, tc);
+        Hc.reset(ctx, (size_t)R * it1 * (it1 + 1));
+        Hc.zero();
+        inv.zero();
     }
-    dim3 cgrid((unsigned)rb, (unsigned)panels);
-    const int sb = (int)ceil_div(tc, 128), rbk = (int)ceil_div(R, 128);
-    EntriesResult out;
-    int j = 0;
-    for (j = 0; j < it; ++j) {                 // step j+1 of the reference: basis V_0..V_j exists
+
+    // step j (0-based): basis V_0..V_j exists; appends V_{j+1} and column j of every H
+    void step(int j) {
         V.emplace_back(new PanelBuf(ctx, n, R));
         PanelBuf& W = *V.back();
+        dim3 cgrid((unsigned)rb, (unsigned)panels);
+        const int rbk = (int)ceil_div(R, 128);
         EpiPlain epi{W.p(), V[j]->p(), 1.0, 0.0};
-        launch_spmm(ctx, A, V[j]->p(), panels, epi, nullptr, R);
+        launch_spmm(ctx, *A, V[j]->p(), panels, epi, nullptr, R);
         auto gs_pass = [&](int mode) {
             for (int l0 = 0; l0 <= j; l0 += MD_CHUNK) {
                 const int nl = std::min(MD_CHUNK, j + 1 - l0);
@@ -266,18 +261,60 @@ inline EntriesResult entries_run(kr_ctx* ctx, const kr_matrix* M, const std::vec
         KR_LAUNCH(ctx, entries_accum_kernel, rbk, 128, 0, Hc.p, it1, j, 0, 0, tc, R, hbuf.p, inv.p, 2);
         KR_LAUNCH(ctx, colscale_kernel, cgrid, COL_THREADS, 0, W.p(), n, tc, inv.p);
         gs_pass(3);
+    }
+
+    // device array of the basis block base pointers (for gather kernels)
+    DevBuf<const double*> block_pointers() {
+        std::vector<const double*> ptrs(V.size());
+        for (size_t l = 0; l < V.size(); ++l) ptrs[l] = V[l]->p();
+        DevBuf<const double*> d(ctx, ptrs.size());
+        d.upload(ptrs.data(), ptrs.size());
+        KR_CUDA(cudaStreamSynchronize(ctx->stream));
+        return d;
+    }
+};
+
+struct EntriesResult { std::vector<double> X; int64_t iter = 0; };
+
+// rows: distinct first indices (1-based, stable order); colof[p]: column of pair p; j2[p]: second index
+inline EntriesResult entries_run(kr_ctx* ctx, const kr_matrix* M, const std::vector<int64_t>& rows,
+                                 const std::vector<int>& colof, const std::vector<int64_t>& j2, int fun,
+                                 double tol, int it) {
+    const int64_t n = M->dev.n;
+    const int R = (int)rows.size(), k = (int)colof.size();
+    const int it1 = it + 1;
+    if (it > 110) fail(KR_ERR_UNSUPPORTED, "function_multiple_entries: it > 110 exceeds the shared-memory solver");
+    ArnoldiBatch B(ctx, M->dev, rows, it);
+    DevBuf<int64_t> dj2(ctx, k);
+    DevBuf<int> dcolof(ctx, k);
+    dj2.upload(j2.data(), k);
+    dcolof.upload(colof.data(), k);
+    DevBuf<double> hist(ctx, (size_t)R * 4 * it1), xfin(ctx, (size_t)R * it1);
+    DevBuf<int> istate(ctx, (size_t)2 * R + 1);
+    hist.zero(); xfin.zero(); istate.zero();
+    int* nfin = istate.p;
+    int* conv = istate.p + R;
+    int* nactive = istate.p + 2 * R;
+    int nact = R;
+    KR_CUDA(cudaMemcpyAsync(nactive, &nact, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    static bool attr_set = false;
+    if (!attr_set) {
+        KR_CUDA(cudaFuncSetAttribute(entries_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_LIMIT));
+        attr_set = true;
+    }
+    EntriesResult out;
+    int j = 0;
+    for (j = 0; j < it; ++j) {                 // step j+1 of the reference
+        B.step(j);
         const int jj = j + 1;
         const size_t smem = (size_t)(2 * jj * (jj | 1) + jj) * sizeof(double);
-        KR_LAUNCH(ctx, entries_step_kernel, R, JAC_THREADS, smem, Hc.p, it1, jj, fun, tol, hist.p, xfin.p, nfin, conv, nactive);
+        KR_LAUNCH(ctx, entries_step_kernel, R, JAC_THREADS, smem, B.Hc.p, it1, jj, fun, tol, hist.p, xfin.p, nfin, conv, nactive);
         KR_CUDA(cudaMemcpyAsync(&nact, nactive, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         KR_CUDA(cudaStreamSynchronize(ctx->stream));
         if (nact <= 0) { ++j; break; }
     }
     out.iter = std::min(j, it);
-    std::vector<const double*> ptrs(V.size());
-    for (size_t l = 0; l < V.size(); ++l) ptrs[l] = V[l]->p();
-    DevBuf<const double*> dptr(ctx, ptrs.size());
-    dptr.upload(ptrs.data(), ptrs.size());
+    DevBuf<const double*> dptr = B.block_pointers();
     DevBuf<double> dX(ctx, k);
     KR_LAUNCH(ctx, entries_gather_kernel, (int)ceil_div(k, 128), 128, 0, dptr.p, n, dj2.p, dcolof.p, xfin.p, nfin, it1, k, dX.p);
     out.X = dX.to_host();

@@ -21,7 +21,7 @@ __all__ = ["slq_trace", "lanczos_krylov", "arnoldi_krylov", "trace_fun_update", 
            "fun_update", "function_multiple_entries", "fun_and_grad_krylov_exp", "fun_and_grad_krylov_fun",
            "normest", "normAm", "select_taylor_degree", "expmv", "ExpmvHandle", "mc_trace", "trace_exp",
            "edge2low_rank", "compute_centrality", "find_top_edges", "find_top_missing_edges",
-           "select_candidate", "krylov_miobi", "greedy_krylov", "KrylovParams"]
+           "select_candidate", "krylov_miobi", "greedy_krylov", "KrylovParams", "fun_and_grad_all_edges", "hessianfcn_exp", "hessianfcn_fun"]
 
 
 def _mat(A, ctx=None):
@@ -530,3 +530,51 @@ def greedy_krylov(A, k, Q=0, centrality=None, order="mult", tol=1e-12, it=None, 
     A = A.tocsr()
     A.eliminate_zeros()
     return edges, rob_variation, A
+
+
+def fun_and_grad_all_edges(X, A, Omega, fun, dfun, tol=1e-8, it=None):
+    """Objective and gradient over a LARGE edge set Omega (config C2: "gradient over all edges").
+
+    Calling fun_and_grad_krylov_fun literally with Omega = all edges makes U an n x n selector and the
+    reference falls into its dense branch (functions/fun_update.m:85-90; SURVEY.md note N1).  The
+    mathematically identical sparse formulation used by the reference's own Hessian callback
+    (functions/hessianfcn_fun.m:5-7) is evaluated instead:
+        Atilde = A + Delta(X, Omega),   gr = -2 * dfun(Atilde)_Omega   (function_multiple_entries, one
+        single-vector Krylov space per distinct row, all advanced by one wide SpMM per step),
+        f = -(trace fun(Atilde) - trace fun(A)) is NOT computed here (use slq_trace / mc_trace on both).
+    Returns gr (len(Omega))."""
+    A = sp.csr_matrix(A).astype(np.float64)
+    n = A.shape[0]
+    Om = np.atleast_2d(np.asarray(Omega)).astype(np.int64)
+    X = np.asarray(X, dtype=np.float64).ravel()
+    D = sp.csr_matrix((X, (Om[:, 0] - 1, Om[:, 1] - 1)), shape=(n, n))
+    At = (A + D + D.T).tocsr()
+    vals, _ = function_multiple_entries(At, Om, dfun, tol, it)
+    return -2.0 * vals
+
+
+def _hessian(X, A, Omega, fun, tol, it):
+    A = sp.csr_matrix(A).astype(np.float64)
+    n = A.shape[0]
+    Om = np.asfortranarray(np.atleast_2d(np.asarray(Omega)).astype(np.int64))
+    X = np.asarray(X, dtype=np.float64).ravel()
+    XX = sp.csr_matrix((X, (Om[:, 0] - 1, Om[:, 1] - 1)), shape=(n, n))
+    M = Matrix((A + XX + XX.T).tocsr())                   # Atilde (functions/hessianfcn_exp.m:4-7)
+    m = Om.shape[0]
+    Hes = np.zeros((m, m), order="F")
+    itv = C.c_int64()
+    check(M.ctx.lib.kr_frechet_hessian(M.ctx.h, M.h, m, _ptr(Om), fun_id(fun), float(tol), int(it), _ptr(Hes),
+                                       C.byref(itv)))
+    if itv.value == int(it):
+        warnings.warn("MULTIPLE_FRECHET_EVAL:: Reached maximum number of iterations")
+    return Hes
+
+
+def hessianfcn_exp(X, A, Omega, tol, it):
+    """Hes = hessianfcn_exp(X,A,Omega,tol,it)  (functions/hessianfcn_exp.m:1-17)."""
+    return _hessian(X, A, Omega, "exp", tol, it)
+
+
+def hessianfcn_fun(X, A, Omega, f, tol, it):
+    """Hes = hessianfcn_fun(X,A,Omega,f,tol,it)  (functions/hessianfcn_fun.m:1-17)."""
+    return _hessian(X, A, Omega, f, tol, it)

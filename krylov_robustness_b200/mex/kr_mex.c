@@ -151,6 +151,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             if (nlhs > 1) plhs[1] = gr; else mxDestroyArray(gr);
         }
         mxFree(om);
+    } else if (!strcmp(op, "hessian")) {                           /* Hes = (Atilde, Omega, f, tol, it) */
+        kr_matrix* M = matrix_of(prhs[0]);
+        mwSize k = mxGetM(prhs[1]);
+        int64_t* om = to_i64(prhs[1], NULL);
+        int64_t it;
+        plhs[0] = mxCreateDoubleMatrix(k, k, mxREAL);
+        chk(kr_frechet_hessian(ctx(), M, (int64_t)k, om, fun_of(prhs[2]), mxGetScalar(prhs[3]),
+                               (int64_t)mxGetScalar(prhs[4]), mxGetPr(plhs[0]), &it));
+        mxFree(om);
     } else if (!strcmp(op, "normest")) {                           /* [e,cnt] = (A,tol) */
         double e; int64_t c;
         chk(kr_normest(ctx(), matrix_of(prhs[0]), mxGetScalar(prhs[1]), &e, &c));

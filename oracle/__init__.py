@@ -22,6 +22,7 @@ from .updates import (trace_fun_update, fun_update, function_multiple_entries,
                       fun_and_grad_krylov_exp, fun_and_grad_krylov_fun, normest)
 from .expmv import expmv, select_taylor_degree, normAm
 from .mctrace import mc_trace, trace_exp, slq_trace
+from .frechet import multiple_frechet_eval, hessianfcn_exp, hessianfcn_fun
 from .greedy import (krylov_miobi, greedy_krylov, find_top_edges, find_top_missing_edges,
                      edge2low_rank, compute_centrality)
 
@@ -31,4 +32,5 @@ __all__ = [
     "normest", "expmv", "select_taylor_degree", "normAm", "mc_trace", "trace_exp",
     "slq_trace", "krylov_miobi", "greedy_krylov", "find_top_edges",
     "find_top_missing_edges", "edge2low_rank", "compute_centrality",
+    "multiple_frechet_eval", "hessianfcn_exp", "hessianfcn_fun",
 ]

@@ -219,6 +219,24 @@ def test_function_multiple_entries_vs_oracle(kr, O, graphs, gname, fun):
     assert np.max(np.abs(X - oX)) <= RTOL * np.max(np.abs(oX))
 
 
+def test_function_multiple_entries_chunked_rows(kr, O, graphs, monkeypatch):
+    """Distinct row indices are processed in chunks on the device; forcing tiny chunks must not change
+    a single bit of the entries (every space is independent)."""
+    A = graphs("transport_Barcelona")
+    n = A.shape[0]
+    rng = np.random.default_rng(9)
+    om = np.stack([rng.integers(1, n + 1, 70), rng.integers(1, n + 1, 70)], 1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        X1, it1 = kr.function_multiple_entries(A, om, "exp", 1e-9, 100)
+        monkeypatch.setenv("KR_ENTRIES_CHUNK_COLS", "16")
+        X2, it2 = kr.function_multiple_entries(A, om, "exp", 1e-9, 100)
+        oX, oit = O.function_multiple_entries(A, om, "exp", 1e-9, 100)
+    assert it1 == it2 == oit
+    assert np.array_equal(X1, X2)
+    assert np.max(np.abs(X1 - oX)) <= RTOL * np.max(np.abs(oX))
+
+
 def test_fun_and_grad_vs_oracle(kr, O, graphs):
     import scipy.linalg as sla
     A = graphs("oregon_A1")
@@ -286,3 +304,44 @@ def test_krylov_miobi_and_centrality(kr, O, graphs):
     oe, orob, _ = O.krylov_miobi(A, 2, E, tol, 100, np.inf, 0, "break")
     e, rob, _ = kr.krylov_miobi(A, 2, E, tol, 100, np.inf, 0, "break")
     assert np.array_equal(e, oe) and abs(rob - orob) <= RTOL * abs(orob)
+
+
+def test_gradient_over_all_edges_vs_dense(kr, graphs):
+    """Config C2 shape: weighted road network, gradient of trace(sinh(A + Delta)) w.r.t. EVERY
+    edge weight = 2*cosh(A + Delta)_ij, from one Krylov space per distinct row index (chunked on the
+    device), against dense ground truth."""
+    import scipy.linalg as sla
+    A = graphs("transport_Rome")
+    n = A.shape[0]
+    L = sp.tril(A, -1).tocoo()
+    Om = np.stack([L.row + 1, L.col + 1], 1)            # all 4831 edges
+    X = 0.1 * L.data * np.random.default_rng(4).random(L.nnz)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gr = kr.fun_and_grad_all_edges(X, A, Om, "sinh", "cosh", 1e-10, 100)
+    D = sp.csr_matrix((X, (Om[:, 0] - 1, Om[:, 1] - 1)), shape=(n, n))
+    At = (A + D + D.T).toarray()
+    lam, Q = np.linalg.eigh(At)
+    C = (Q * np.cosh(lam)) @ Q.T
+    true = -2.0 * C[Om[:, 0] - 1, Om[:, 1] - 1]
+    assert np.max(np.abs(gr - true)) <= 1e-8 * np.max(np.abs(true))
+
+
+@pytest.mark.parametrize("gname,fun", [("grid_England", "exp"), ("oregon_A0", "cosh"), ("grid_Mexico", "sinh")])
+def test_hessian_callbacks_vs_oracle(kr, O, graphs, gname, fun):
+    """Row f3: hessianfcn_exp / hessianfcn_fun over multiple_frechet_eval."""
+    A = graphs(gname)
+    if gname == "oregon_A0":
+        A = (A / 8.0).tocsr()
+    Om, X = _omega(A, 9, 2, min_degree=2)
+    Om[3] = [Om[0, 0], Om[5, 1]]               # pairs sharing a row space and a column space
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if fun == "exp":
+            oH = O.hessianfcn_exp(X, A, Om, 1e-10, 60)
+            H = kr.hessianfcn_exp(X, A, Om, 1e-10, 60)
+        else:
+            oH = O.hessianfcn_fun(X, A, Om, fun, 1e-10, 60)
+            H = kr.hessianfcn_fun(X, A, Om, fun, 1e-10, 60)
+    assert H.shape == oH.shape and np.array_equal(H, H.T)
+    assert np.max(np.abs(H - oH)) <= RTOL * np.max(np.abs(oH))

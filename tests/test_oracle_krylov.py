@@ -232,3 +232,25 @@ def test_fun_and_grad_fun_vs_dense(graphs):
     assert np.linalg.norm(gr - grtrue) <= 1e-5 * np.linalg.norm(grtrue)
     with pytest.raises(ValueError, match="not Hermitian"):
         O.fun_and_grad_krylov_fun(X, sp.triu(A).tocsr(), Om, "sinh", "cosh", dfA, 1e-8, 100)
+
+
+def test_hessian_vs_dense_frechet(graphs):
+    """hessianfcn_exp against the dense Frechet derivative expm([A E; 0 A]) (the reference's debug == 3
+    identity, multiple_frechet_eval.m:176-180)."""
+    A = graphs("grid_Sweden")
+    n = A.shape[0]
+    Ad = A.toarray()
+    Om, X = _random_omega(A, 5, 0, min_degree=2)
+    H = O.hessianfcn_exp(X, A, Om, 1e-11, 100)
+    D = np.zeros((n, n))
+    for (a, b), x in zip(Om, X):
+        D[a - 1, b - 1] = x
+        D[b - 1, a - 1] = x
+    At = Ad + D
+    for j, (h, k) in enumerate(Om):
+        E = np.zeros((n, n))
+        E[h - 1, k - 1] = 1.0
+        F = sla.expm(np.block([[At, E], [np.zeros((n, n)), At]]))[:n, n:]
+        for l in range(j, len(Om)):
+            assert abs(H[j, l] + 2 * F[Om[l, 0] - 1, Om[l, 1] - 1]) <= 1e-9 * np.abs(H).max()
+    assert np.array_equal(H, H.T)
