@@ -73,6 +73,7 @@ void kr_ctx_destroy(kr_ctx* c) {
     c->trim();
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
     if (c->cublas) cublasDestroy(c->cublas);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -335,10 +336,67 @@ int kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, in
         if (!ctx || !A || !Z) fail(KR_ERR_ARG, "kr_slq_trace: null argument");
         if (fun < 0 || fun > 2) fail(KR_ERR_ARG, "unsupported function selector");
         KR_CUDA(cudaSetDevice(ctx->device));
-        PanelBuf W(ctx, A->dev.n, (int)k);
-        upload_cm(ctx, Z, ldz, W);
-        SlqResult R = slq_run(ctx, A, W, (int)m, fun, alpha || beta);
-        slq_finish(R, m, tr, vals, alpha, beta);
+        const int64_t n = A->dev.n;
+        if (ldz < n) fail(KR_ERR_ARG, "The block vector b has wrong number of rows");
+        // Probe columns are independent, so the block is processed in column chunks: chunk c+1 is copied
+        // host -> device and re-laid out on a second stream while chunk c runs its m Lanczos steps.
+        const int64_t chunk = 128;
+        const int64_t nch = std::max<int64_t>(1, ceil_div(k, chunk));
+        if (!ctx->copy_stream) KR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        std::vector<std::unique_ptr<PanelBuf>> W(nch);
+        std::vector<std::unique_ptr<DevBuf<double>>> stage(nch);
+        std::vector<cudaEvent_t> ready(nch, nullptr);
+        for (int64_t c = 0; c < nch; ++c) {
+            const int64_t c0 = c * chunk, cw = std::min(chunk, k - c0);
+            W[c].reset(new PanelBuf(ctx, n, (int)cw));
+            stage[c].reset(new DevBuf<double>(ctx, (size_t)std::max<int64_t>(n * cw, 1)));
+        }
+        KR_CUDA(cudaStreamSynchronize(ctx->stream));     // pool buffers may still be in use by earlier work
+        auto issue_copy = [&](int64_t c) {
+            const int64_t c0 = c * chunk, cw = std::min(chunk, k - c0);
+            if (n > 0 && cw > 0) {
+                KR_CUDA(cudaMemcpy2DAsync(stage[c]->p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
+                                          n * sizeof(double), cw, cudaMemcpyHostToDevice, ctx->copy_stream));
+                ctx->counters[3] += n * cw * (int64_t)sizeof(double);
+            }
+            cm_to_panel(ctx, stage[c]->p, n, *W[c], ctx->copy_stream);
+            KR_CUDA(cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming));
+            KR_CUDA(cudaEventRecord(ready[c], ctx->copy_stream));
+        };
+        std::vector<double> all_vals((size_t)k), all_a, all_b;
+        if (alpha || beta) { all_a.resize((size_t)m * k); all_b.resize((size_t)m * k); }
+        try {
+            issue_copy(0);
+            for (int64_t c = 0; c < nch; ++c) {
+                const int64_t c0 = c * chunk, cw = std::min(chunk, k - c0);
+                KR_CUDA(cudaStreamWaitEvent(ctx->stream, ready[c], 0));
+                SlqJob job(ctx, A, *W[c], (int)m, fun, alpha || beta);      // enqueue chunk c (no host sync)
+                if (c + 1 < nch) issue_copy(c + 1);                          // overlaps with chunk c (also when the
+                                                                             // host buffer is pageable and the copy blocks)
+                SlqResult R = job.collect();
+                for (int64_t q = 0; q < cw; ++q) all_vals[(size_t)(c0 + q)] = R.vals[(size_t)q];
+                if (alpha || beta)
+                    for (int64_t j = 0; j < m; ++j)
+                        for (int64_t q = 0; q < cw; ++q) {
+                            all_a[(size_t)(j * k + c0 + q)] = R.alpha[(size_t)(j * cw + q)];
+                            all_b[(size_t)(j * k + c0 + q)] = R.beta[(size_t)(j * cw + q)];
+                        }
+            }
+        } catch (...) {
+            cudaStreamSynchronize(ctx->copy_stream);
+            for (auto e : ready) if (e) cudaEventDestroy(e);
+            throw;
+        }
+        KR_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        for (auto e : ready) if (e) cudaEventDestroy(e);
+        SlqResult T;
+        T.vals = all_vals;
+        T.alpha = all_a;
+        T.beta = all_b;
+        double s = 0.0;
+        for (int64_t q = 0; q < k; ++q) s += all_vals[(size_t)q];
+        T.tr = k ? s / (double)k : 0.0;
+        slq_finish(T, m, tr, vals, alpha, beta);
     });
 }
 

@@ -86,6 +86,7 @@ struct kr_ctx {
     int num_sms = 148;
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host<->device staging that overlaps compute (created on first use)
     cublasHandle_t cublas = nullptr;
     cusolverDnHandle_t cusolver = nullptr;
     // counters: launches, spmm launches, matvecs, h2d bytes, d2h bytes

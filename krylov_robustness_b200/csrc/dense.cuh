@@ -66,10 +66,11 @@ panel_to_cm_kernel(const double* __restrict__ src, int64_t n, int cols, double* 
     }
 }
 
-inline void cm_to_panel(kr_ctx* ctx, const double* src_dev, int64_t ld, PanelBuf& dst) {
+inline void cm_to_panel(kr_ctx* ctx, const double* src_dev, int64_t ld, PanelBuf& dst, cudaStream_t stream = nullptr) {
     if (dst.n == 0 || dst.panels == 0) return;
     dim3 grid((unsigned)ceil_div(dst.n, 64), (unsigned)dst.panels);
-    KR_LAUNCH(ctx, cm_to_panel_kernel, grid, 256, 0, src_dev, ld, dst.n, dst.cols, dst.p());
+    cm_to_panel_kernel<<<grid, 256, 0, stream ? stream : ctx->stream>>>(src_dev, ld, dst.n, dst.cols, dst.p());
+    check_launch(ctx, "cm_to_panel_kernel");
 }
 inline void panel_to_cm(kr_ctx* ctx, const PanelBuf& src, double* dst_dev, int64_t ld) {
     if (src.n == 0 || src.panels == 0) return;

@@ -1,18 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
+python -m pytest tests/test_gpu_spmm.py -m gpu -q -x -k "not full_size" > gpurun_out/pytest_o.log 2>&1; tail -2 gpurun_out/pytest_o.log
+KR_BENCH_EDGES=0 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_o.log 2>&1
 python - <<PY
-import torch
-p=torch.cuda.get_device_properties(0); print('L2',p.L2_cache_size/2**20,'MB')
-PY
-run() { # name persist_mb
-  KR_BENCH_EDGES=0 KR_SPMM_L2PERSIST=$2 python bench.py --steps 2 --warmup 3 > gpurun_out/bench_n_$1.log 2>&1
-  python - <<PY
 import json
-l=[x for x in open('gpurun_out/bench_n_$1.log') if x.startswith('{')]
-d=json.loads(l[-1]); print('$1 value',d['value'],'ms/step',d['ms_per_step'],'spmm ms',d['roofline']['ms_per_launch'],'launches',d['roofline']['launches_timed'])
+l=[x for x in open('gpurun_out/bench_o.log') if x.startswith('{')]
+d=json.loads(l[-1]); print('value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e']['value'],'e2e ms',d['e2e']['ms_per_step'],'tr',d['trace_estimate'],d['e2e']['trace_estimate'])
 PY
-}
-run p0 0
-run p32 32
-run p64 64
-run p96 96
+tail -3 gpurun_out/bench_o.log | cut -c1-300
