@@ -44,7 +44,14 @@ struct PanelBlock {                // non-owning view of a panel-major block
 };
 
 __device__ __forceinline__ double2 ld_x(const double* p) {      // gathered operand: keep in L1/L2
-#if defined(KR_X_LOAD_CG)
+#if defined(KR_X_EVICT_LAST)
+    // tuning build: mark gathered X lines evict_last in L2 so the streaming CSR / Y traffic cannot displace them
+    double2 r;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    return r;
+#elif defined(KR_X_LOAD_CG)
     return __ldcg(reinterpret_cast<const double2*>(p));          // tuning build: L2 only, no L1 allocation
 #elif defined(KR_X_LOAD_NOALLOC)
     double2 r;

@@ -1,10 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_spmm.py -m gpu -q -x -k "not full_size" > gpurun_out/pytest_o.log 2>&1; tail -2 gpurun_out/pytest_o.log
-KR_BENCH_EDGES=0 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_o.log 2>&1
+KR_BENCH_EDGES=0 KR_B200_LIB=$PWD/krylov_robustness_b200/libkrylov_b200_el.so python bench.py --steps 2 --warmup 3 > gpurun_out/bench_p_el.log 2>&1
 python - <<PY
 import json
-l=[x for x in open('gpurun_out/bench_o.log') if x.startswith('{')]
-d=json.loads(l[-1]); print('value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e']['value'],'e2e ms',d['e2e']['ms_per_step'],'tr',d['trace_estimate'],d['e2e']['trace_estimate'])
+l=[x for x in open('gpurun_out/bench_p_el.log') if x.startswith('{')]
+d=json.loads(l[-1]); print('evict_last value',d['value'],'ms/step',d['ms_per_step'],'spmm ms',d['roofline']['ms_per_launch'])
 PY
-tail -3 gpurun_out/bench_o.log | cut -c1-300
