@@ -111,13 +111,13 @@ inline int col_row_blocks(int64_t n) { return (int)ceil_div(n, COL_ROWS_PER_CTA)
 // deterministic CTA reduction of NV values per (threadIdx.x % LPT) class -> lanes 0..LPT-1 of warp 0
 template <int NV>
 __device__ __forceinline__ void col_cta_reduce(double (&v)[NV], double* smem) {
-    cta_reduce_by_sub<NV>(v, smem);      // same 8-warp shape as the SpMM CTA
+    cta_reduce_by_sub<NV>(v, smem);      // 8 warps (COL_THREADS = 256)
 }
 
 // partial[rb][col] = sum over the CTA's rows of X(r,col)^2.  grid = (row_blocks, panels)
 __global__ void __launch_bounds__(COL_THREADS)
 colnorm2_kernel(const double* __restrict__ X, int64_t n, double* __restrict__ partial, int total_cols) {
-    __shared__ double smem[SPMM_WARPS * LPT * 2];
+    __shared__ double smem[COL_WARPS * LPT * 2];
     const int q = blockIdx.y, sub = threadIdx.x % LPT;
     const double* Xp = X + (int64_t)q * n * PW;
     const int64_t r0 = (int64_t)blockIdx.x * COL_ROWS_PER_CTA;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(COL_THREADS)
 combine3_norm_kernel(const double* __restrict__ Y, const double* __restrict__ U1,
                      const double* U0, double* W, int64_t n, const double* __restrict__ coef,
                      int total_cols, double* __restrict__ partial) {
-    __shared__ double smem[SPMM_WARPS * LPT * 2];
+    __shared__ double smem[COL_WARPS * LPT * 2];
     const int q = blockIdx.y, sub = threadIdx.x % LPT;
     const int64_t po = (int64_t)q * n * PW;
     const int col = q * PW + sub * 2;

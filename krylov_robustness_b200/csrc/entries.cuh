@@ -20,7 +20,7 @@ struct PtrChunk { const double* v[MD_CHUNK]; };
 // partial[(rb*nl + l)*tc + col] = sum_rows V_l(r,col) * W(r,col),  l < nl <= 8
 __global__ void __launch_bounds__(COL_THREADS)
 multi_dot_kernel(PtrChunk V, int nl, const double* __restrict__ W, int64_t n, int tc, double* __restrict__ partial) {
-    __shared__ double smem[SPMM_WARPS * LPT * 2];
+    __shared__ double smem[COL_WARPS * LPT * 2];
     const int q = blockIdx.y, sub = threadIdx.x % LPT;
     const int64_t po = (int64_t)q * n * PW;
     const int64_t r0 = (int64_t)blockIdx.x * COL_ROWS_PER_CTA;

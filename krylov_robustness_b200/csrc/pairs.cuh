@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(COL_THREADS)
 pair_update_kernel(double* __restrict__ Y, const double* __restrict__ P, const double* __restrict__ C,
                    int64_t n, const double* __restrict__ coef, int ncand, double* __restrict__ partial) {
     constexpr int NV = MODE == 0 ? 8 : 4;
-    __shared__ double smem[SPMM_WARPS * LPT * NV];
+    __shared__ double smem[COL_WARPS * LPT * NV];
     __shared__ double cf[LPT][12];
     const int q = blockIdx.y, sub = threadIdx.x % LPT;
     if (threadIdx.x < LPT * 12) {

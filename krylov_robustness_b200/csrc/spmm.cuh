@@ -26,7 +26,11 @@ namespace kr {
 constexpr int PW = KR_PW;          // panel width (columns): 8 (64 B row-tiles) or 16 (128 B row-tiles)
 constexpr int LPT = PW / 2;        // lanes per row-tile (one double2 per lane)
 static_assert(PW == 8 || PW == 16, "panel width must be 8 or 16");
-constexpr int SPMM_THREADS = 256;  // 8 warps
+#ifndef KR_SPMM_THREADS
+#define KR_SPMM_THREADS 256
+#endif
+constexpr int SPMM_THREADS = KR_SPMM_THREADS;  // warps per SpMM CTA = SPMM_THREADS / 32
+constexpr int COL_WARPS = 8;                   // the streaming per-column kernels always use 256 threads
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
 #ifndef KR_SPMM_MIN_CTAS
 #define KR_SPMM_MIN_CTAS 4
@@ -73,8 +77,8 @@ __device__ __forceinline__ double2 shfl_xor2(double2 v, int off) {
 }
 
 // Sum NV per-thread values over all threads of the CTA that share (lane % LPT), deterministically,
-// and hand the totals to lanes 0..LPT-1 of warp 0.  smem: SPMM_WARPS * LPT * NV doubles.
-template <int NV>
+// and hand the totals to lanes 0..LPT-1 of warp 0.  smem: WARPS * LPT * NV doubles.
+template <int NV, int WARPS = COL_WARPS>
 __device__ __forceinline__ void cta_reduce_by_sub(double (&v)[NV], double* smem) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -93,7 +97,7 @@ __device__ __forceinline__ void cta_reduce_by_sub(double (&v)[NV], double* smem)
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             double s = 0.0;
-            for (int w = 0; w < SPMM_WARPS; ++w) s += smem[(w * LPT + lane) * NV + i];
+            for (int w = 0; w < WARPS; ++w) s += smem[(w * LPT + lane) * NV + i];
             v[i] = s;
         }
     }
@@ -150,7 +154,7 @@ struct EpiDot {
         st_stream(Y + (int64_t)r * PW + sub * 2, y);
     }
     __device__ __forceinline__ void finish(int tile, int panel, double* smem) {
-        cta_reduce_by_sub<2>(acc, smem);
+        cta_reduce_by_sub<2, SPMM_WARPS>(acc, smem);
         if (threadIdx.x < LPT) {
             double* o = partial + (int64_t)tile * total_cols + panel * PW + threadIdx.x * 2;
             o[0] = acc[0];
@@ -194,7 +198,7 @@ struct EpiGram2 {
         st_stream(Y + o, y);
     }
     __device__ __forceinline__ void finish(int tile, int panel, double* smem) {
-        cta_reduce_by_sub<8>(acc, smem);
+        cta_reduce_by_sub<8, SPMM_WARPS>(acc, smem);
         if (threadIdx.x < LPT) {
             double* o = partial + ((int64_t)tile * ncand + panel * LPT + threadIdx.x) * 8;
 #pragma unroll
@@ -391,7 +395,7 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
                 v[0] += a.x;
                 v[1] += a.y;
             }
-            cta_reduce_by_sub<2>(v, red);                  // totals in threads 0..3
+            cta_reduce_by_sub<2, SPMM_WARPS>(v, red);      // totals in threads 0..LPT-1
             double2 acc = make_double2(v[0], v[1]);
             if (!HAS_VAL) {
                 acc.x *= A.uval;
