@@ -2,10 +2,10 @@
 // Reference: functions/expmv.m, functions/select_taylor_degree.m, functions/normAm.m.
 //
 // The Taylor inner loop (expmv.m:75-88) is ONE fused SpMM launch per term (b' = coef*(A-mu I)b,
-// f += b', per-row abs-sums of b' and f) plus one tiny reduction kernel that evaluates the
-// early-termination test c1 + c2 <= tol*||f||_inf ON THE DEVICE and raises a flag; later launches
-// of the stage see the flag and return immediately, so a whole expmv call is enqueued without a
-// single host round-trip.  The 1-norm power sequence of normAm (A >= 0: e <- A'e, exact) is computed
+// f += b', row abs-sums of b' and f); the early-termination test c1 + c2 <= tol*||f||_inf is evaluated
+// ON THE DEVICE by the last CTA to finish (inside the SpMM itself when q <= 16, else in one small
+// reduction kernel) and raises a flag; later launches of the stage see the flag and return
+// immediately, so a whole expmv call is enqueued without a single host round-trip.  The 1-norm power sequence of normAm (A >= 0: e <- A'e, exact) is computed
 // once for all p = 1..p_max (9 SpMVs instead of 44; the reported mv stays the reference's count).
 #pragma once
 #include <cmath>
@@ -16,27 +16,7 @@
 namespace kr {
 
 // ---------------------------------------------------------------------------------- norms
-// partial[b] = max over the CTA's rows of sum_panels ra[panel][r]
-__global__ void rowsum_max_partial_kernel(const double* __restrict__ ra, int64_t n, int panels,
-                                          double* __restrict__ partial, const int* __restrict__ done) {
-    if (done && *done) return;
-    __shared__ double red[8];
-    double m = 0.0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int q = 0; q < panels; ++q) s += ra[(int64_t)q * n + r];
-        m = fmax(m, s);
-    }
-    for (int off = 16; off; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
-        partial[blockIdx.x] = m;
-    }
-}
-
-// ra[panel][r] = sum of |X(r, c)| over the panel's 8 columns
+// ra[panel][r] = sum of |X(r, c)| over the panel's PW columns
 __global__ void rowabs_kernel(const double* __restrict__ X, int64_t n, int panels, double* __restrict__ ra) {
     const int64_t total = n * panels;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -48,37 +28,55 @@ __global__ void rowabs_kernel(const double* __restrict__ X, int64_t n, int panel
     }
 }
 
-struct TaylorCtl {
-    double c1;        // running ||b||_inf of the previous term
-    double c2, nf;    // scratch
-    int done;         // early-termination flag of the current stage
-    int mv;           // products actually computed
-};
-
-// mode 0: c1 = max(partial_b)            (stage start, expmv.m:74)
-// mode 1: c2 = max(partial_b), nf = max(partial_f); mv++; test (expmv.m:78-86)
-__global__ void taylor_ctl_kernel(TaylorCtl* ctl, const double* __restrict__ pb, const double* __restrict__ pf,
-                                  int nparts, int mode, int full_term, double tol) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (mode == 0) {
-        double m = 0.0;
-        for (int i = 0; i < nparts; ++i) m = fmax(m, pb[i]);
-        ctl->c1 = m;
-        ctl->done = 0;
-        return;
+// Several panels: out of the per-panel row abs-sums, ||b'||_inf and ||f||_inf (max over rows of the sum
+// over panels); the last CTA to finish evaluates the termination test (expmv.m:78-86).
+// mode 0 (stage start, expmv.m:74): c1 = ||b||_inf from rab only, done = 0.
+__global__ void __launch_bounds__(256)
+taylor_norms_ctl_kernel(const double* __restrict__ rab, const double* __restrict__ raf, int64_t n, int panels,
+                        double* __restrict__ pb, double* __restrict__ pf, TaylorCtl* ctl, int mode, int full_term,
+                        double tol) {
+    if (mode == 1 && ctl->done) return;
+    __shared__ double red[16];
+    __shared__ int last;
+    double mb = 0.0, mf = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        double sb = 0.0, sf = 0.0;
+        for (int q = 0; q < panels; ++q) {
+            sb += rab[(int64_t)q * n + r];
+            if (mode == 1) sf += raf[(int64_t)q * n + r];
+        }
+        mb = fmax(mb, sb);
+        mf = fmax(mf, sf);
     }
-    if (ctl->done) return;
-    double c2 = 0.0, nf = 0.0;
-    for (int i = 0; i < nparts; ++i) {
-        c2 = fmax(c2, pb[i]);
-        nf = fmax(nf, pf[i]);
+    for (int off = 16; off; off >>= 1) {
+        mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, off));
+        mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, off));
     }
-    ctl->mv += 1;
-    ctl->c2 = c2;
-    ctl->nf = nf;
-    if (!full_term) {
-        if (ctl->c1 + c2 <= tol * nf) ctl->done = 1;
-        else ctl->c1 = c2;
+    if ((threadIdx.x & 31) == 0) { red[2 * (threadIdx.x >> 5)] = mb; red[2 * (threadIdx.x >> 5) + 1] = mf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mb = fmax(mb, red[2 * w]); mf = fmax(mf, red[2 * w + 1]); }
+        pb[blockIdx.x] = mb;
+        pf[blockIdx.x] = mf;
+        __threadfence();
+        last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double c2 = 0.0, nf = 0.0;
+        for (unsigned i = 0; i < gridDim.x; ++i) {          // fixed order (max is order independent anyway)
+            c2 = fmax(c2, ((volatile double*)pb)[i]);
+            nf = fmax(nf, ((volatile double*)pf)[i]);
+        }
+        ctl->ticket = 0u;
+        if (mode == 0) {
+            ctl->c1 = c2;
+            ctl->done = 0;
+        } else {
+            taylor_decide(ctl, c2, nf, full_term, tol);
+        }
+        __threadfence();
     }
 }
 
@@ -352,20 +350,24 @@ inline ExpmvInfo expmv_dev(kr_ctx* ctx, const kr_matrix* M, double t, PanelBuf& 
     const int egrid = (int)std::min<int64_t>(ctx->num_sms * 8, std::max<int64_t>(1, ceil_div(total, 256)));
     double* b = B.p();
     double* bn = Bn.p();
+    const bool fused = panels == 1;                    // q <= PW: one launch per Taylor term
+    const int spmm_ctas = M->dev.ntiles;
     for (int64_t i = 0; i < info.s; ++i) {
         KR_LAUNCH(ctx, rowabs_kernel, egrid, 256, 0, b, n, panels, rab.p);
-        KR_LAUNCH(ctx, rowsum_max_partial_kernel, nparts, 256, 0, rab.p, n, panels, pb.p, (const int*)nullptr);
-        KR_LAUNCH(ctx, taylor_ctl_kernel, 1, 32, 0, ctl.p, pb.p, pf.p, nparts, 0, (int)full_term, tol);
+        KR_LAUNCH(ctx, taylor_norms_ctl_kernel, nparts, 256, 0, rab.p, raf.p, n, panels, pb.p, pf.p, ctl.p, 0, (int)full_term, tol);
         const int* done = &ctl.p->done;
         for (int64_t k = 1; k <= info.m; ++k) {
             EpiTaylor epi;
             epi.Bn = bn; epi.Bo = b; epi.F = F.p(); epi.rab = rab.p; epi.raf = raf.p;
             epi.coef = t / ((double)info.s * (double)k);
             epi.mu = mu;
+            epi.ctl = fused ? ctl.p : nullptr;
+            epi.total_ctas = spmm_ctas;
+            epi.full_term = (int)full_term;
+            epi.tol = tol;
             launch_spmm(ctx, M->dev, b, panels, epi, done, 0);
-            KR_LAUNCH(ctx, rowsum_max_partial_kernel, nparts, 256, 0, rab.p, n, panels, pb.p, done);
-            KR_LAUNCH(ctx, rowsum_max_partial_kernel, nparts, 256, 0, raf.p, n, panels, pf.p, done);
-            KR_LAUNCH(ctx, taylor_ctl_kernel, 1, 32, 0, ctl.p, pb.p, pf.p, nparts, 1, (int)full_term, tol);
+            if (!fused)
+                KR_LAUNCH(ctx, taylor_norms_ctl_kernel, nparts, 256, 0, rab.p, raf.p, n, panels, pb.p, pf.p, ctl.p, 1, (int)full_term, tol);
             std::swap(b, bn);
         }
         KR_LAUNCH(ctx, stage_end_kernel, egrid, 256, 0, F.p(), b, total, eta);

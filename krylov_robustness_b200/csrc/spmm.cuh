@@ -207,23 +207,55 @@ struct EpiGram2 {
     }
 };
 
-// expmv Taylor term (functions/expmv.m:77-80): b' = coef*(A*b - mu*b); f += b';
-// rowabs_b[panel][r] = sum over the panel's 8 columns of |b'|, same for f (matrix inf-norms are the
-// max over rows of the sum over panels; reduced by expmv_norms_kernel).
-// Skips all work once *done != 0 (early termination decided on the device).
+// Device-side control block of one expmv call (expmv.cuh): the early-termination test of
+// functions/expmv.m:83 is evaluated on the device so that a whole call is enqueued without host syncs.
+struct TaylorCtl {
+    double c1;                         // ||b||_inf of the previous term
+    double c2, nf;                     // last ||b'||_inf, ||f||_inf (diagnostics)
+    int done;                          // early-termination flag of the current stage
+    int mv;                            // products actually computed
+    unsigned long long mb_bits, mf_bits;   // running maxima (bit patterns of non-negative doubles)
+    unsigned int ticket;               // CTAs that have finished the current term
+};
+
+__device__ __forceinline__ void taylor_decide(TaylorCtl* ctl, double c2, double nf, int full_term, double tol) {
+    ctl->mv += 1;
+    ctl->c2 = c2;
+    ctl->nf = nf;
+    if (!full_term) {
+        if (ctl->c1 + c2 <= tol * nf) ctl->done = 1;
+        else ctl->c1 = c2;
+    }
+}
+
+// expmv Taylor term (functions/expmv.m:77-80): b' = coef*(A*b - mu*b); f += b'.  The matrix inf-norms
+// (max over rows of the abs-sum over ALL columns) are needed for the termination test:
+//  * one panel (q <= PW, the mc_trace case): row sums are complete inside the CTA; maxima go through
+//    atomicMax on the bit patterns (max of non-negative doubles is order independent, hence still
+//    deterministic) and the LAST CTA to finish evaluates the test - one launch per Taylor term;
+//  * several panels: rowabs_b[panel][r] / rowabs_f[panel][r] are written and reduced by
+//    taylor_norms_ctl_kernel (expmv.cuh) - two launches per term.
+// Every launch returns immediately once *done != 0.
 struct EpiTaylor {
     double* __restrict__ Bn;       // output b' panel
     const double* __restrict__ Bo; // input b panel (== X)
     double* __restrict__ F;        // f panel (read-modify-write)
-    double* __restrict__ rab;      // rowabs of b' for this panel [n]
+    double* __restrict__ rab;      // rowabs of b' for this panel [n]   (multi-panel mode)
     double* __restrict__ raf;      // rowabs of f  for this panel [n]
     double coef, mu;
+    TaylorCtl* ctl;                // non-null: single-panel fused control
+    int total_ctas, full_term;
+    double tol;
+    double mb, mf;
     __device__ __forceinline__ void init(int q, int64_t stride) {
         Bn += q * stride;
         Bo += q * stride;
         F += q * stride;
-        rab += q * (stride / PW);
-        raf += q * (stride / PW);
+        if (!ctl) {
+            rab += q * (stride / PW);
+            raf += q * (stride / PW);
+        }
+        mb = mf = 0.0;
     }
     double2 xr, fr;
     __device__ __forceinline__ void pre(int r, int sub) {
@@ -245,19 +277,50 @@ struct EpiTaylor {
         *reinterpret_cast<double2*>(F + o) = f;
         st_stream(Bn + o, y);
         double ab = fabs(y.x) + fabs(y.y), af = fabs(f.x) + fabs(f.y);
-        // the four slot-0 lanes of a row hold its 8 columns: fold over sub.  m = ballot of the
-        // lanes that entered the epilogue (the four subs of a row always enter together).
+        // the LPT slot-0 lanes of a row hold its PW columns: fold over sub.  m = ballot of the lanes that
+        // entered the epilogue (the subs of a row always enter together).
 #pragma unroll
         for (int off = 1; off < LPT; off <<= 1) {
             ab += __shfl_xor_sync(m, ab, off);
             af += __shfl_xor_sync(m, af, off);
         }
-        if (sub == 0) {
+        if (ctl) {
+            mb = fmax(mb, ab);
+            mf = fmax(mf, af);
+        } else if (sub == 0) {
             rab[r] = ab;
             raf[r] = af;
         }
     }
-    __device__ __forceinline__ void finish(int, int, double*) {}
+    __device__ __forceinline__ void finish(int, int, double* smem) {
+        if (!ctl) return;
+        // CTA maxima -> global maxima -> last CTA decides
+        double a = mb, b = mf;
+        for (int off = 16; off; off >>= 1) {
+            a = fmax(a, __shfl_xor_sync(0xffffffffu, a, off));
+            b = fmax(b, __shfl_xor_sync(0xffffffffu, b, off));
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) { smem[2 * warp] = a; smem[2 * warp + 1] = b; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < SPMM_WARPS; ++w) { a = fmax(a, smem[2 * w]); b = fmax(b, smem[2 * w + 1]); }
+            atomicMax(&ctl->mb_bits, (unsigned long long)__double_as_longlong(a));
+            atomicMax(&ctl->mf_bits, (unsigned long long)__double_as_longlong(b));
+            __threadfence();
+            const unsigned t = atomicAdd(&ctl->ticket, 1u);
+            if (t == (unsigned)total_ctas - 1u) {
+                __threadfence();
+                const double c2 = __longlong_as_double((long long)atomicAdd(&ctl->mb_bits, 0ull));
+                const double nf = __longlong_as_double((long long)atomicAdd(&ctl->mf_bits, 0ull));
+                taylor_decide(ctl, c2, nf, full_term, tol);
+                ctl->mb_bits = 0ull;
+                ctl->mf_bits = 0ull;
+                ctl->ticket = 0u;
+                __threadfence();
+            }
+        }
+    }
 };
 
 // ------------------------------------------------------------------------------- kernel
