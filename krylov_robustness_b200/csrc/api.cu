@@ -200,7 +200,7 @@ int kr_matrix_set_edges(kr_matrix* A, int64_t count, const int64_t* ii, const in
             N.row_ptr[i + 1] = (int64_t)N.col.size();
         }
         H = std::move(N);
-        analyse_and_upload(A);
+        analyse_and_upload(A, /*keep_symmetric=*/true);
     });
 }
 

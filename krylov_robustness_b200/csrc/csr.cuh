@@ -205,12 +205,19 @@ struct kr_matrix {
 
 namespace kr {
 
-inline void analyse_and_upload(kr_matrix* M) {
+// keep_symmetric: the caller guarantees the edit preserved symmetry (kr_matrix_set_edges writes both
+// triangles), so the O(nnz) transpose + comparison is skipped and ||A||_1 is the max row abs-sum.
+inline void analyse_and_upload(kr_matrix* M, bool keep_symmetric = false) {
     CsrHost& H = M->host;
     canonicalize(H);
-    const int64_t n = H.n, nnz = H.row_ptr[n];
-    CsrHost T = transpose(H);
-    M->symmetric = (T.row_ptr == H.row_ptr) && (T.col == H.col) && (T.val == H.val);
+    const int64_t n = H.n;
+    CsrHost T;
+    if (keep_symmetric && M->symmetric) {
+        M->symmetric = true;
+    } else {
+        T = transpose(H);
+        M->symmetric = (T.row_ptr == H.row_ptr) && (T.col == H.col) && (T.val == H.val);
+    }
     M->nonnegative = true;
     M->trace = 0.0;
     for (int64_t i = 0; i < n; ++i)
@@ -218,13 +225,13 @@ inline void analyse_and_upload(kr_matrix* M) {
             if (H.val[p] < 0) M->nonnegative = false;
             if (H.col[p] == i) M->trace += H.val[p];
         }
-    M->norm1 = 0.0;   // max column abs-sum = max row abs-sum of A'
+    const CsrHost& C = M->symmetric ? H : T;       // column abs-sums of A = row abs-sums of A'
+    M->norm1 = 0.0;
     for (int64_t i = 0; i < n; ++i) {
         double s = 0;
-        for (int64_t p = T.row_ptr[i]; p < T.row_ptr[i + 1]; ++p) s += std::abs(T.val[p]);
+        for (int64_t p = C.row_ptr[i]; p < C.row_ptr[i + 1]; ++p) s += std::abs(C.val[p]);
         M->norm1 = std::max(M->norm1, s);
     }
-    (void)nnz;
     upload_csr(M->ctx, H, M->dev);
     if (!M->symmetric) upload_csr(M->ctx, T, M->devT);
     else { M->devT = CsrDev(); }

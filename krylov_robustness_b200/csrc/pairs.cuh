@@ -33,8 +33,10 @@ __global__ void pair_init_kernel(double* __restrict__ C, int64_t n, const int64_
 template <int MODE>
 __global__ void __launch_bounds__(COL_THREADS)
 pair_update_kernel(double* __restrict__ Y, const double* __restrict__ P, const double* __restrict__ C,
-                   int64_t n, const double* __restrict__ coef, int ncand, double* __restrict__ partial) {
+                   int64_t n, const double* __restrict__ coef, int ncand, double* __restrict__ partial,
+                   const int* __restrict__ panel_active) {
     constexpr int NV = MODE == 0 ? 8 : 4;
+    if (!panel_active[blockIdx.y]) return;            // all candidates of this panel have converged
     __shared__ double smem[COL_WARPS * LPT * NV];
     __shared__ double cf[LPT][12];
     const int q = blockIdx.y, sub = threadIdx.x % LPT;
@@ -293,6 +295,16 @@ pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict
     }
 }
 
+// panel_active[q] = any candidate of panel q still iterating (lets the SpMM and the update passes skip
+// whole panels: candidates converge after 3..11 steps)
+__global__ void pair_panel_active_kernel(const int* __restrict__ active, int ncp, int* __restrict__ panel_active) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * LPT >= ncp) return;
+    int any = 0;
+    for (int i = 0; i < LPT; ++i) any |= active[q * LPT + i];
+    panel_active[q] = any;
+}
+
 struct PairResult {
     std::vector<double> Xm;
     std::vector<int> iter, lucky;
@@ -315,7 +327,7 @@ inline void pairs_run_chunk(kr_ctx* ctx, const kr_matrix* M, const int64_t* E_de
     const int nparts = std::max(rb, A.ntiles);
     DevBuf<double> partial(ctx, (size_t)nparts * ncp * 8), Gsum(ctx, (size_t)ncp * 8);
     DevBuf<double> dstate(ctx, (size_t)ncp * (4 + 4 + 4 + 4 + 12 + 2 + 1) + (size_t)ncp * it * 12);
-    DevBuf<int> istate(ctx, (size_t)ncp * 3 + 1);
+    DevBuf<int> istate(ctx, (size_t)ncp * 3 + 1), pact(ctx, panels);
     dstate.zero();
     istate.zero();
     PairState st;
@@ -345,6 +357,7 @@ inline void pairs_run_chunk(kr_ctx* ctx, const kr_matrix* M, const int64_t* E_de
     KR_CUDA(cudaMemcpyAsync(st.active, act.data(), (size_t)ncp * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     int nact = ncand;
     KR_CUDA(cudaMemcpyAsync(st.nactive, &nact, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    KR_LAUNCH(ctx, pair_panel_active_kernel, (int)ceil_div(panels, 128), 128, 0, st.active, ncp, pact.p);
     KR_CUDA(cudaStreamSynchronize(ctx->stream));
 
     double* C = B0.p();
@@ -364,19 +377,20 @@ inline void pairs_run_chunk(kr_ctx* ctx, const kr_matrix* M, const int64_t* E_de
         const int first = (j == 1);
         EpiGram2 epi;
         epi.Y = Y; epi.P = P; epi.C = C; epi.partial = partial.p; epi.ncand = ncp;
-        launch_spmm(ctx, A, C, panels, epi, nullptr, cols);
+        launch_spmm(ctx, A, C, panels, epi, nullptr, cols, pact.p);
         sum_partials(ctx, partial.p, A.ntiles, ncp * 8, Gsum.p);
         KR_LAUNCH(ctx, pair_coef1_kernel, cb, 128, 0, st, Gsum.p, first);
-        KR_LAUNCH(ctx, pair_update_kernel<0>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ncp, partial.p);
+        KR_LAUNCH(ctx, pair_update_kernel<0>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ncp, partial.p, pact.p);
         sum_partials(ctx, partial.p, rb, ncp * 8, Gsum.p);
         KR_LAUNCH(ctx, pair_coef2_kernel, cb, 128, 0, st, Gsum.p, first);
-        KR_LAUNCH(ctx, pair_update_kernel<1>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ncp, partial.p);
+        KR_LAUNCH(ctx, pair_update_kernel<1>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ncp, partial.p, pact.p);
         sum_partials(ctx, partial.p, rb, ncp * 4, Gsum.p);
         const int nn = 2 * j;
         const size_t smem = (size_t)(2 * nn * (nn | 1) + 2 * nn) * sizeof(double);
         if (smem > JAC_SMEM_LIMIT)
             fail(KR_ERR_UNSUPPORTED, "trace_fun_update_edges: projected size %d exceeds the shared-memory solver", nn);
         KR_LAUNCH(ctx, pair_step_kernel, ncand, JAC_THREADS, smem, st, Gsum.p, Y, n, j);
+        KR_LAUNCH(ctx, pair_panel_active_kernel, (int)ceil_div(panels, 128), 128, 0, st.active, ncp, pact.p);
         // rotate blocks: previous <- current, current <- W
         double* oldP = P ? P : spare;
         P = C;

@@ -409,7 +409,7 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict
 template <class Epi, bool HAS_VAL, int U>
 __global__ void __launch_bounds__(SPMM_THREADS, SPMM_MIN_CTAS)
 spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t panel_stride,
-            const int* __restrict__ done, int panels, int ppc, int panel0) {
+            const int* __restrict__ done, int panels, int ppc, int panel0, const int* __restrict__ panel_active) {
     if (done && *done) return;
     __shared__ double red[SPMM_WARPS * LPT * 8];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -435,6 +435,7 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
     const int panel_first = panel0 + blockIdx.y * ppc;
     const int panel_end = min(panels, panel_first + ppc);
     for (int panel = panel_first; panel < panel_end; ++panel) {
+        if (panel_active && !panel_active[panel]) continue;   // every column of this panel has converged
         Epi epi = epi_proto;
         epi.init(panel, panel_stride);
         const double* Xp = X + (int64_t)panel * panel_stride;
@@ -483,7 +484,7 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
 // Host-side launcher.  Epilogues carry panel-0 pointers; init() advances them to the CTA's panel.
 template <class Epi>
 inline void launch_spmm(kr_ctx* ctx, const CsrDev& A, const double* X, int panels, const Epi& epi,
-                        const int* done = nullptr, int logical_cols = -1) {
+                        const int* done = nullptr, int logical_cols = -1, const int* panel_active = nullptr) {
     if (A.ntiles == 0 || panels == 0) return;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->timing) {
@@ -508,11 +509,11 @@ inline void launch_spmm(kr_ctx* ctx, const CsrDev& A, const double* X, int panel
     const int64_t ps = (int64_t)A.n * PW;
     auto launch = [&](dim3 grid, int npanels, int panel0) {
         if (A.pattern_only) {
-            if (variant == 8) spmm_kernel<Epi, false, 8><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0);
-            else spmm_kernel<Epi, false, 4><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0);
+            if (variant == 8) spmm_kernel<Epi, false, 8><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0, panel_active);
+            else spmm_kernel<Epi, false, 4><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0, panel_active);
         } else {
-            if (variant == 8) spmm_kernel<Epi, true, 8><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0);
-            else spmm_kernel<Epi, true, 4><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0);
+            if (variant == 8) spmm_kernel<Epi, true, 8><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0, panel_active);
+            else spmm_kernel<Epi, true, 4><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, npanels, ppc, panel0, panel_active);
         }
     };
     launch(dim3((unsigned)A.ntiles, (unsigned)((panels + ppc - 1) / ppc)), panels, 0);
