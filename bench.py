@@ -42,7 +42,19 @@ def build_graph():
     A = power_law_graph(N_NODES, NNZ, 2.2, GRAPH_SEED)
     lam = spectral_radius_estimate(A, 30)
     A = A * (1.0 / lam)          # uniform value -> stored pattern-only on the device
-    return A.tocsr(), lam
+    A = A.tocsr()
+    reorder = os.environ.get("KR_BENCH_REORDER", "")      # experiment knob: symmetric relabelling of the nodes
+    if reorder:
+        if reorder == "degree":
+            perm = np.argsort(-np.diff(A.indptr), kind="stable")
+        elif reorder == "rcm":
+            from scipy.sparse.csgraph import reverse_cuthill_mckee
+            perm = reverse_cuthill_mckee(A, symmetric_mode=True)
+        else:
+            raise SystemExit("KR_BENCH_REORDER must be degree or rcm")
+        A = A[perm][:, perm].tocsr()
+        A.sort_indices()
+    return A, lam
 
 
 def config_dict(world):

@@ -1,8 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_krylov.py -m gpu -q -x > gpurun_out/pytest_s.log 2>&1; tail -3 gpurun_out/pytest_s.log
-python scripts/replay_unweighted.py --graphs oregon_A0,oregon_A8,transport_Rome 2>/dev/null | python -c "
-import sys, json
-for l in sys.stdin:
-    d=json.loads(l); print(d['graph'], d['method'], round(d['time_s'],4), round(d.get('edges_per_s',0)))
-"
+for v in degree rcm; do
+  KR_BENCH_EDGES=0 KR_BENCH_REORDER=$v python bench.py --steps 2 --warmup 3 > gpurun_out/bench_t_$v.log 2>&1
+  python - <<PY
+import json
+l=[x for x in open('gpurun_out/bench_t_$v.log') if x.startswith('{')]
+d=json.loads(l[-1]); print('$v value',d['value'],'ms/step',d['ms_per_step'],'spmm ms',d['roofline']['ms_per_launch'],'tr',d['trace_estimate'])
+PY
+done
