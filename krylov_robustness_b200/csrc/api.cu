@@ -338,22 +338,31 @@ int kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, in
         KR_CUDA(cudaSetDevice(ctx->device));
         const int64_t n = A->dev.n;
         if (ldz < n) fail(KR_ERR_ARG, "The block vector b has wrong number of rows");
+        if (k <= 0) fail(KR_ERR_ARG, "kr_slq_trace: no probe columns");
         // Probe columns are independent, so the block is processed in column chunks: chunk c+1 is copied
-        // host -> device and re-laid out on a second stream while chunk c runs its m Lanczos steps.
-        const int64_t chunk = 128;
-        const int64_t nch = std::max<int64_t>(1, ceil_div(k, chunk));
+        // host -> device and re-laid out on a second stream while chunk c runs its m Lanczos steps, and
+        // chunk c+1 is enqueued before the host waits for chunk c (the GPU never drains between chunks).
+        // The first chunk is small so that compute starts after a few milliseconds of upload.
+        std::vector<int64_t> cstart, cwidth;
+        for (int64_t c0 = 0; c0 < k;) {
+            const int64_t cw = std::min<int64_t>(k - c0, cstart.empty() ? 2 * PW : (cstart.size() == 1 ? 6 * PW : 8 * PW));
+            cstart.push_back(c0);
+            cwidth.push_back(cw);
+            c0 += cw;
+        }
+        if (cstart.empty()) { cstart.push_back(0); cwidth.push_back(0); }
+        const int64_t nch = (int64_t)cstart.size();
         if (!ctx->copy_stream) KR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         std::vector<std::unique_ptr<PanelBuf>> W(nch);
         std::vector<std::unique_ptr<DevBuf<double>>> stage(nch);
         std::vector<cudaEvent_t> ready(nch, nullptr);
         for (int64_t c = 0; c < nch; ++c) {
-            const int64_t c0 = c * chunk, cw = std::min(chunk, k - c0);
-            W[c].reset(new PanelBuf(ctx, n, (int)cw));
-            stage[c].reset(new DevBuf<double>(ctx, (size_t)std::max<int64_t>(n * cw, 1)));
+            W[c].reset(new PanelBuf(ctx, n, (int)cwidth[c]));
+            stage[c].reset(new DevBuf<double>(ctx, (size_t)std::max<int64_t>(n * cwidth[c], 1)));
         }
         KR_CUDA(cudaStreamSynchronize(ctx->stream));     // pool buffers may still be in use by earlier work
         auto issue_copy = [&](int64_t c) {
-            const int64_t c0 = c * chunk, cw = std::min(chunk, k - c0);
+            const int64_t c0 = cstart[c], cw = cwidth[c];
             if (n > 0 && cw > 0) {
                 KR_CUDA(cudaMemcpy2DAsync(stage[c]->p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
                                           n * sizeof(double), cw, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -365,25 +374,33 @@ int kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, in
         };
         std::vector<double> all_vals((size_t)k), all_a, all_b;
         if (alpha || beta) { all_a.resize((size_t)m * k); all_b.resize((size_t)m * k); }
+        auto harvest = [&](int64_t c, SlqJob& job) {
+            const int64_t c0 = cstart[c], cw = cwidth[c];
+            SlqResult R = job.collect();
+            for (int64_t q = 0; q < cw; ++q) all_vals[(size_t)(c0 + q)] = R.vals[(size_t)q];
+            if (alpha || beta)
+                for (int64_t j = 0; j < m; ++j)
+                    for (int64_t q = 0; q < cw; ++q) {
+                        all_a[(size_t)(j * k + c0 + q)] = R.alpha[(size_t)(j * cw + q)];
+                        all_b[(size_t)(j * k + c0 + q)] = R.beta[(size_t)(j * cw + q)];
+                    }
+        };
         try {
             issue_copy(0);
+            std::unique_ptr<SlqJob> prev;
             for (int64_t c = 0; c < nch; ++c) {
-                const int64_t c0 = c * chunk, cw = std::min(chunk, k - c0);
                 KR_CUDA(cudaStreamWaitEvent(ctx->stream, ready[c], 0));
-                SlqJob job(ctx, A, *W[c], (int)m, fun, alpha || beta);      // enqueue chunk c (no host sync)
-                if (c + 1 < nch) issue_copy(c + 1);                          // overlaps with chunk c (also when the
-                                                                             // host buffer is pageable and the copy blocks)
-                SlqResult R = job.collect();
-                for (int64_t q = 0; q < cw; ++q) all_vals[(size_t)(c0 + q)] = R.vals[(size_t)q];
-                if (alpha || beta)
-                    for (int64_t j = 0; j < m; ++j)
-                        for (int64_t q = 0; q < cw; ++q) {
-                            all_a[(size_t)(j * k + c0 + q)] = R.alpha[(size_t)(j * cw + q)];
-                            all_b[(size_t)(j * k + c0 + q)] = R.beta[(size_t)(j * cw + q)];
-                        }
+                std::unique_ptr<SlqJob> job(new SlqJob(ctx, A, *W[c], (int)m, fun, alpha || beta));   // enqueue chunk c
+                job->mark();
+                if (c + 1 < nch) issue_copy(c + 1);      // overlaps with chunk c (also when the host buffer is
+                                                         // pageable and the copy call blocks)
+                if (prev) harvest(c - 1, *prev);
+                prev = std::move(job);
             }
+            if (prev) harvest(nch - 1, *prev);
         } catch (...) {
             cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamSynchronize(ctx->stream);
             for (auto e : ready) if (e) cudaEventDestroy(e);
             throw;
         }

@@ -78,14 +78,33 @@ struct SlqJob {
         KR_LAUNCH(ctx, slq_quadrature_kernel, (int)ceil_div(cols, 64), 64, 0, alpha.p, beta.p, nrm2, m, cols, tc, fun, vals.p);
     }
 
+    // non-blocking completion marker: lets a caller enqueue the next job before waiting for this one
+    cudaEvent_t finished = nullptr;
+    void mark() {
+        KR_CUDA(cudaEventCreateWithFlags(&finished, cudaEventDisableTiming));
+        KR_CUDA(cudaEventRecord(finished, ctx->stream));
+    }
+    ~SlqJob() { if (finished) cudaEventDestroy(finished); }
+
     SlqResult collect() {
         SlqResult R;
-        std::vector<double> v = vals.to_host();
+        std::vector<double> v(vals.count);
+        if (finished) {
+            // wait for THIS job only (later jobs may already be queued behind it), then copy on the copy stream
+            KR_CUDA(cudaEventSynchronize(finished));
+            cudaStream_t cs = ctx->copy_stream ? ctx->copy_stream : ctx->stream;
+            KR_CUDA(cudaMemcpyAsync(v.data(), vals.p, v.size() * sizeof(double), cudaMemcpyDeviceToHost, cs));
+            KR_CUDA(cudaStreamSynchronize(cs));
+            ctx->counters[4] += (int64_t)(v.size() * sizeof(double));
+        } else {
+            v = vals.to_host();
+        }
         R.vals.assign(v.begin(), v.begin() + cols);
         double s = 0.0;
         for (int c = 0; c < cols; ++c) s += R.vals[c];
         R.tr = cols ? s / cols : 0.0;
         if (want_ab) {
+            if (finished) KR_CUDA(cudaStreamSynchronize(ctx->stream));
             std::vector<double> a = alpha.to_host(), b = beta.to_host();
             R.alpha.resize((size_t)m * cols);
             R.beta.resize((size_t)m * cols);

@@ -117,3 +117,41 @@ def test_empty_and_degenerate_inputs(kr, graphs):
     Y = Mz @ np.ones((300, 3))
     assert np.all(Y == 0)
     assert Mz.info()["nnz"] == 0
+
+
+def test_slq_breakdown_and_duplicates(kr):
+    """Lanczos breakdown (beta = 0: probe supported on an isolated node / an eigenvector) and a CSR input
+    with duplicate, unsorted entries (summed like MATLAB's sparse())."""
+    import oracle as O
+    import scipy.sparse as sp
+    rng = np.random.default_rng(0)
+    n = 400
+    B = sp.random(n - 3, n - 3, density=0.02, random_state=2)
+    B = ((B + B.T) * 0.5).tocsr()
+    A = sp.block_diag([B, sp.csr_matrix((3, 3))], format="csr")     # three isolated nodes
+    Z = rng.standard_normal((n, 5))
+    Z[:, 0] = 0.0
+    Z[n - 1, 0] = 2.0                                               # A z = 0: breakdown at step 1
+    tr, vals, al, be = kr.slq_trace(A, Z, 12, "exp", return_details=True)
+    otr, ovals, oal, obe = O.slq_trace(A, Z, 12, "exp")
+    assert vals[0] == 4.0 == ovals[0] and be[0, 0] == 0.0
+    assert np.max(np.abs(vals - ovals)) <= 1e-10 * np.max(np.abs(ovals))
+    # duplicates + unsorted columns in the raw CSR arrays
+    rows = np.array([0, 0, 0, 1, 2, 2]); cols = np.array([2, 1, 2, 0, 0, 0]); data = np.array([1.0, 3.0, 0.5, 3.0, 1.0, 0.5])
+    indptr = np.array([0, 3, 4, 6]); 
+    Araw = sp.csr_matrix((data, cols, indptr), shape=(3, 3))        # not canonical on purpose
+    M = kr.Matrix.__new__(kr.Matrix)
+    import ctypes as C
+    ctx = kr.Context.default()
+    h = C.c_void_p()
+    rp = indptr.astype(np.int64); ci = cols.astype(np.int64)
+    kr._lib.check(ctx.lib.kr_matrix_create(ctx.h, 3, 6, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p),
+                                           data.ctypes.data_as(C.c_void_p), C.byref(h)))
+    M.ctx, M.h, M.n, M.shape = ctx, h, 3, (3, 3)
+    X = np.eye(3)
+    dense = np.zeros((3, 3))
+    for r in range(3):
+        for p in range(indptr[r], indptr[r + 1]):
+            dense[r, cols[p]] += data[p]
+    assert np.array_equal(M @ X, dense)
+    assert M.info()["symmetric"] and M.info()["nnz"] == 4
