@@ -146,7 +146,8 @@ inline void gemm(kr_ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k,
 inline void gram_tn(kr_ctx* ctx, const double* V, int64_t ldv, int64_t c, const double* W, int64_t ldw, int64_t b,
                     int64_t n, double* G) {
     if (c == 0 || b == 0) return;
-    if (b > 128) {
+    static const bool force_cublas = getenv("KR_GRAM_CUBLAS") != nullptr;   // A/B switch for debugging
+    if (b > 128 || force_cublas) {
         gemm(ctx, true, false, c, b, n, 1.0, V, ldv, W, ldw, 0.0, G, c);
         return;
     }
