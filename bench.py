@@ -350,7 +350,14 @@ def run_ours(args):
                          else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "algorithmic_bytes_per_launch": b_spmm, "ms_per_launch": per_launch_ms,
                          "launches_timed": spmm_launches,
-                         "share_of_step": spmm_ms / ms_dev, "traffic": traffic},
+                         "share_of_step": spmm_ms / ms_dev, "traffic": traffic,
+                         # what actually binds on a random power-law graph: every
+                         # (nonzero, column) operand crosses L2 -> SM once; the pure-gather ceiling on a
+                         # 128 MB window was measured with scripts/l2_gather.cu
+                         "gather": {"bytes_per_launch": 8.0 * nnz * k,
+                                    "achieved_tb_per_s": 8.0 * nnz * k / (per_launch_ms * 1e-3) / 1e12,
+                                    "microbench_ceiling_tb_per_s": 14.8,
+                                    "source": "profiles/r01_l2_gather_microbench.json"}},
             "secondary": secondary,
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": "oracle.slq_trace (NumPy/SciPy port of the reference path) on 4 probes x %d steps "

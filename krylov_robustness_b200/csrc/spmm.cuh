@@ -65,6 +65,19 @@ __device__ __forceinline__ double2 ld_x(const double* p) {      // gathered oper
     return __ldg(reinterpret_cast<const double2*>(p));
 #endif
 }
+// L2 prefetch of a row-tile of X that a later round will gather: the demand gathers are latency-bound
+// (every lane already holds U row-tiles in flight in registers) and 39 % of them miss L2 because one
+// panel of X is as large as L2; a prefetch holds no register, so the DRAM part of the latency is paid
+// KR_SPMM_PF rounds ahead of the demand load (measured: 7.6 -> 6.6 ms per k=512 SpMM).
+#ifndef KR_SPMM_PF
+#define KR_SPMM_PF 1
+#endif
+#ifndef KR_SPMM_PF_EPI
+#define KR_SPMM_PF_EPI 0
+#endif
+__device__ __forceinline__ void prefetch_x(const double* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(double* p, double2 v) {
@@ -117,6 +130,9 @@ struct EpiPlain {
         X += q * stride;
     }
     double2 xr;
+    __device__ __forceinline__ void prefetch(int r) const {      // row-local operands of a later row -> L2
+        if (mu != 0.0) prefetch_x(X + (int64_t)r * PW);
+    }
     __device__ __forceinline__ void pre(int r, int sub) {
         if (mu != 0.0) xr = *reinterpret_cast<const double2*>(X + (int64_t)r * PW + sub * 2);
     }
@@ -145,6 +161,7 @@ struct EpiDot {
         acc[0] = acc[1] = 0.0;
     }
     double2 xr;
+    __device__ __forceinline__ void prefetch(int r) const { prefetch_x(X + (int64_t)r * PW); }
     __device__ __forceinline__ void pre(int r, int sub) {
         xr = *reinterpret_cast<const double2*>(X + (int64_t)r * PW + sub * 2);
     }
@@ -180,6 +197,10 @@ struct EpiGram2 {
         for (int i = 0; i < 8; ++i) acc[i] = 0.0;
     }
     double2 cr, pr;
+    __device__ __forceinline__ void prefetch(int r) const {
+        prefetch_x(C + (int64_t)r * PW);
+        if (P) prefetch_x(P + (int64_t)r * PW);
+    }
     __device__ __forceinline__ void pre(int r, int sub) {
         const int64_t o = (int64_t)r * PW + sub * 2;
         cr = *reinterpret_cast<const double2*>(C + o);
@@ -258,6 +279,10 @@ struct EpiTaylor {
         mb = mf = 0.0;
     }
     double2 xr, fr;
+    __device__ __forceinline__ void prefetch(int r) const {
+        if (mu != 0.0) prefetch_x(Bo + (int64_t)r * PW);
+        prefetch_x(F + (int64_t)r * PW);
+    }
     __device__ __forceinline__ void pre(int r, int sub) {
         const int64_t o = (int64_t)r * PW + sub * 2;
         if (mu != 0.0) xr = *reinterpret_cast<const double2*>(Bo + o);
@@ -335,9 +360,16 @@ constexpr size_t SPMM_SMEM_VALUED = SPMM_SMEM_PATTERN + SPMM_CAP * sizeof(double
 // unit that limits this kernel; profiles/r01_d_*).
 template <bool HAS_VAL, int U>
 __device__ __forceinline__ double2 gather_accumulate(int p_first, int p_end, int stride, const int* __restrict__ scol,
-                                                     const double* __restrict__ sval, const double* __restrict__ xs) {
+                                                     const double* __restrict__ sval, const double* __restrict__ xs,
+                                                     const double* __restrict__ xpanel, int pf_sub) {
     double2 acc0 = make_double2(0.0, 0.0), acc1 = acc0;
     for (int p = p_first; p < p_end; p += U * stride) {
+#if KR_SPMM_PF > 0
+        {   // lane `pf_sub` of the group prefetches slot u = pf_sub of the round KR_SPMM_PF ahead
+            const int qpf = p + (KR_SPMM_PF * U + pf_sub) * stride;
+            if (pf_sub < U && qpf < p_end) prefetch_x(xpanel + (int64_t)scol[qpf] * PW);
+        }
+#endif
         double2 x[U];
         double v[U];
 #pragma unroll
@@ -389,7 +421,23 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict
         }
         const bool emit = valid && slot == 0;
         if (emit) epi.pre(row, sub);    // row-local operands: issue their loads before the gathers
-        double2 acc = gather_accumulate<HAS_VAL, U>(p0 + slot, p1, S, scol, sval, xs);
+#if KR_SPMM_PF > 0
+        {   // the row this lane group serves KR_SPMM_PF passes from now: prefetch its first KR_SPMM_PF rounds
+            const int rn = rr + KR_SPMM_PF * SPMM_WARPS * RPW;
+            if (rn < t.count) {
+                const int q0 = srp[rn], q1 = srp[rn + 1];
+#if KR_SPMM_PF_EPI
+                if (slot == 0 && sub == 0) epi.prefetch(srid[rn]);
+#endif
+#pragma unroll
+                for (int k = 0; k < KR_SPMM_PF; ++k) {
+                    const int q = q0 + slot + (k * U + sub) * S;
+                    if (sub < U && q < q1) prefetch_x(Xp + (int64_t)scol[q] * PW);
+                }
+            }
+        }
+#endif
+        double2 acc = gather_accumulate<HAS_VAL, U>(p0 + slot, p1, S, scol, sval, xs, Xp, sub);
 #pragma unroll
         for (int off = LPT; off < L; off <<= 1) {
             double2 o = shfl_xor2(acc, off);
@@ -455,7 +503,7 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
                         for (int p = threadIdx.x; p < cn; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + c0 + p);
                     __syncthreads();
                 }
-                double2 a = gather_accumulate<HAS_VAL, U>(slot, cn, SPMM_THREADS / LPT, scol, sval, Xp + sub * 2);
+                double2 a = gather_accumulate<HAS_VAL, U>(slot, cn, SPMM_THREADS / LPT, scol, sval, Xp + sub * 2, Xp, sub);
                 v[0] += a.x;
                 v[1] += a.y;
             }

@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""Replay of the reference's weighted tuning / rewire / add experiments
+(Tests/test_weighted_sinh_lbfgs.m:6-214, ..._cosh_lbfgs.m, ..._exp_lbfgs.m) on the device engine -
+row f4 of SURVEY.md section 8, config C2.
+
+  python scripts/replay_weighted.py [--graphs grid_England,grid_Mexico] [--fun sinh] [--oracle]
+
+Per graph (fixtures already carry the scripts' preprocessing; A <- A / max(A), :52): eigenvector
+centrality (:59), tol = 1e-6 f(normest(A,1e-2)) (:60-66), search-space reduction by centrality
+(find_top_edges / find_top_missing_edges, :70,124-125,168) and by the gradient entries
+df(A)(i,j) (function_multiple_entries, :82), then
+
+    min  -trace f(A + X_E)   s.t.  sum(x) <= total_weight,  LB <= x <= UB          (:190-198)
+
+with objective + gradient from fun_and_grad_krylov_fun / _exp (the hot path).  MATLAB's fmincon
+(interior point, L-BFGS Hessian) has no twin here; SciPy's SLSQP plays its part - the comparison that
+matters is device callbacks vs oracle callbacks under the SAME optimiser (--oracle): identical iterates
+as long as f and the gradient agree to the optimiser's tolerance.  Prints one JSON line per
+(graph, method, impl).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+import scipy.optimize as so
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DERIV = {"sinh": "cosh", "cosh": "sinh", "exp": "exp"}
+
+
+def select_edges(P, A, c, method, df, tol_df, it, modifiable, search_space):
+    """Search-space reductions of test_weighted_sinh_lbfgs.m:68-187; P = kr or oracle module."""
+    def top(E, keep):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            vals, _ = P.function_multiple_entries(A, E, df, tol_df, it)
+        ind = np.argsort(-vals, kind="stable")[:keep]
+        return E[ind], vals[ind]
+
+    dense = A.toarray()
+    if method == "tuning":
+        E, dfA = top(P.find_top_edges(A, c, search_space, "min"), modifiable)
+        w = dense[E[:, 0] - 1, E[:, 1] - 1]
+        return E, dfA, -0.5 * w, w
+    if method == "rewire":
+        E1, d1 = top(P.find_top_edges(A, c, search_space // 2, "min"), modifiable // 2)
+        E2, d2 = top(P.find_top_missing_edges(A, c, search_space // 2, "min"), modifiable // 2)
+        w = dense[E1[:, 0] - 1, E1[:, 1] - 1]
+        return (np.vstack([E1, E2]), np.concatenate([d1, d2]), np.concatenate([-w, np.zeros(len(E2))]),
+                np.concatenate([w, np.ones(len(E2))]))
+    E, dfA = top(P.find_top_missing_edges(A, c, search_space, "min"), modifiable)
+    return E, dfA, np.zeros(len(E)), np.ones(len(E))
+
+
+def run(P, A, fun, method, args):
+    n = A.shape[0]
+    df = DERIV[fun]
+    c = P.compute_centrality(A, "eig")
+    nrm = P.normest(A, 1e-2)
+    nrm = float(nrm[0] if isinstance(nrm, tuple) else nrm)
+    tol = args.tol * float(getattr(np, fun)(nrm))
+    tol_df = args.tol * float(getattr(np, df)(nrm))
+    t0 = time.perf_counter()
+    E, dfA, LB, UB = select_edges(P, A, c, method, df, tol_df, args.it, args.edges, args.search_space)
+    calls = [0]
+
+    def fg(x):
+        calls[0] += 1
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if fun == "exp":
+                f, g = P.fun_and_grad_krylov_exp(x, A, E, dfA, tol, args.it)
+            else:
+                f, g = P.fun_and_grad_krylov_fun(x, A, E, fun, df, dfA, tol, args.it)
+        return float(f), np.asarray(g, dtype=np.float64)
+
+    res = so.minimize(fg, np.zeros(len(E)), jac=True, method="SLSQP", bounds=list(zip(LB, UB)),
+                      constraints=[{"type": "ineq", "fun": lambda x: args.weight - x.sum(),
+                                    "jac": lambda x: -np.ones_like(x)}],
+                      options={"maxiter": args.maxiter, "ftol": 1e-9})
+    dt = time.perf_counter() - t0
+    lam = np.linalg.eigvalsh(A.toarray())
+    trfA = float(np.sum(getattr(np, fun)(lam)))
+    return {"n": n, "method": method, "fun": fun, "edges": E.tolist(), "x": res.x.tolist(), "fval": float(res.fun),
+            "rel_gain": float(-res.fun / trfA), "iterations": int(res.nit), "callbacks": calls[0], "time_s": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--graphs", default="grid_England,grid_Mexico")
+    ap.add_argument("--fun", default="sinh", choices=list(DERIV))
+    ap.add_argument("--methods", default="tuning,rewire,add")
+    ap.add_argument("--edges", type=int, default=30)          # modifiable_edges (:11)
+    ap.add_argument("--search-space", type=int, default=100)  # search_space (:12)
+    ap.add_argument("--weight", type=float, default=10.0)     # total_weight (:14)
+    ap.add_argument("--tol", type=float, default=1e-6)        # tol_param (:7)
+    ap.add_argument("--it", type=int, default=100)
+    ap.add_argument("--maxiter", type=int, default=200)       # (:26)
+    ap.add_argument("--oracle", action="store_true")
+    args = ap.parse_args()
+    import krylov_robustness_b200 as kr
+    from conftest import load_graph
+    impls = [("b200", kr)]
+    if args.oracle:
+        import oracle as O
+        impls.append(("oracle", O))
+    for name in args.graphs.split(","):
+        A = load_graph(name)
+        A = (A / A.max()).tocsr()
+        for method in args.methods.split(","):
+            out = {}
+            for tag, P in impls:
+                r = run(P, A, args.fun, method, args)
+                r.update(graph=name, impl=tag)
+                out[tag] = r
+                print(json.dumps({k: v for k, v in r.items() if k not in ("edges", "x")}), flush=True)
+            if len(out) == 2:
+                a, b = out["b200"], out["oracle"]
+                print(json.dumps({"graph": name, "method": method, "compare": "b200 vs oracle",
+                                  "same_edges": a["edges"] == b["edges"],
+                                  "rel_fval_diff": abs(a["fval"] - b["fval"]) / abs(b["fval"]),
+                                  "max_x_diff": float(np.max(np.abs(np.array(a["x"]) - np.array(b["x"])))),
+                                  "speedup": b["time_s"] / a["time_s"]}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
