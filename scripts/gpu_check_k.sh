@@ -1,5 +1,3 @@
 #!/bin/bash
-# prefetch build: GPU test tier + default bench
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --timeout=900 > gpurun_out/pytest_k.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_k.log; tail -4 gpurun_out/pytest_k.log
-python bench.py > gpurun_out/bench_k.json 2> gpurun_out/bench_k.err; echo; tail -c 3000 gpurun_out/bench_k.json
+python -m pytest tests/test_gpu_krylov.py -m gpu -q --timeout=900 -k "trace_fun_update" > gpurun_out/pytest_k3.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_k3.log; tail -6 gpurun_out/pytest_k3.log; grep "^E " gpurun_out/pytest_k3.log | head

@@ -95,10 +95,20 @@ def test_trace_fun_update_edges_vs_oracle(kr, O, graphs, gname, fun, sign):
         ox, oit, olucky = O.trace_fun_update(A, U, B, tol, 100, 0, fun)
         assert it[h] == oit and bool(lucky[h]) == bool(olucky), (h, it[h], oit)
         assert abs(x[h] - ox) <= RTOL * abs(ox), (h, x[h], ox)
-    # the single-candidate entry point goes through the wide-block path: same answers
+    # the single-candidate entry point: U = [e_i e_j], B = [0 b; b 0] is recognised and takes the pair kernels
     U, B = edge_UB(n, int(E[0, 0]), int(E[0, 1]), sign)
     x1, it1, _ = kr.trace_fun_update(A, U, B, tol, 100, 0, fun)
     assert it1 == it[0] and abs(x1 - x[0]) <= RTOL * abs(x[0])
+    # the same rank-2 update written with a rotated basis (U Q, Q' B Q) is NOT of that shape and takes the
+    # general wide-block path (cuSOLVER QR / eigen-solves): same update matrix, same answer
+    th = 0.3
+    Q = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    Bq = Q.T @ B @ Q
+    Bq = 0.5 * (Bq + Bq.T)                       # exactly symmetric (the device path insists on it)
+    x2, it2, _ = kr.trace_fun_update(A, np.asarray(U) @ Q, Bq, tol, 100, 0, fun)
+    ox2, oit2, _ = O.trace_fun_update(A, np.asarray(U) @ Q, Bq, tol, 100, 0, fun)
+    assert it2 == oit2 and abs(x2 - ox2) <= RTOL * abs(ox2)
+    assert abs(x2 - x[0]) <= 1e-8 * abs(x[0])
 
 
 def test_trace_fun_update_edges_with_leaf_endpoints(kr, O, graphs):
