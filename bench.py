@@ -199,6 +199,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    from krylov_robustness_b200.parallel import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local)          # before any pinned allocation: keep the probes socket-local
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -338,7 +340,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(world),
             "trace_estimate": tr_value, "lambda_scale": lam,
-            "clocks": clocks,
+            "clocks": clocks, "numa": numa,
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": (h1["h2d_bytes"] - h0["h2d_bytes"]) // e2e_steps,
                     "d2h_bytes_per_step": (h1["d2h_bytes"] - h0["d2h_bytes"]) // e2e_steps + 8,

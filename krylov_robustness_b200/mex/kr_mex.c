@@ -3,9 +3,10 @@
  * libkrylov_b200.so (include/krylov_b200.h).  The wrappers in ../matlab/ keep the reference's
  * function signatures and call   varargout = kr_mex('<op>', args...).
  *
- * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has neither mex.h nor mkoctfile
- * (SURVEY.md section 0).  It is a thin marshaller on purpose - every line with arithmetic in it lives
- * behind the C ABI and is exercised from Python (tests/).  Build where MATLAB/Octave exists:
+ * The build image has neither mex.h nor mkoctfile; tests/test_mex_gateway.py
+ * compiles this file against a stub of the MEX API (tests/mex_stub/) and runs it on the GPU tier.  It is
+ * a thin marshaller on purpose - every line with arithmetic in it lives behind the C ABI and is
+ * exercised from Python (tests/).  Build where MATLAB/Octave exists:
  *   mex -I../../include kr_mex.c -L.. -lkrylov_b200          (MATLAB)
  *   mkoctfile --mex -I../../include kr_mex.c -L.. -lkrylov_b200   (Octave)
  *

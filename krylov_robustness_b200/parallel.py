@@ -90,3 +90,32 @@ def sharded_probe_trace(local_sum_fn, k_total):
     lo, hi = shard_bounds(k_total)
     s = float(local_sum_fn(lo, hi)) if hi > lo else 0.0
     return allreduce_sum(s) / float(k_total)
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (CPU affinity, hence first-touch page placement of everything allocated afterwards,
+    pinned staging buffers included) to the NUMA node the GPU hangs off.  On a two-socket host a rank whose
+    pinned probe block lives on the far socket uploads it several times slower.  Host plumbing only; returns a
+    small dict for logging, or None when the topology is not exposed (single node, container without sysfs)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"gpu": bdf, "node": node, "cpus": cpulist, "bound_cpus": len(allowed)}
+    except Exception:
+        return None
+
