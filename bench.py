@@ -217,6 +217,10 @@ def run_ours(args):
         cw = min(64, k - c0)
         Zpin.numpy()[c0:c0 + cw] = kr.Dense(n, cw, ctx).fill_rademacher(PROBE_SEED, col_offset=rank * k + c0).download().T
     zptr = Zpin.data_ptr()
+    # the same probes as int8 signs (Rademacher probes carry one bit per entry): kr_slq_trace_sign
+    Zpin8 = torch.empty((k, n), dtype=torch.int8, pin_memory=True)
+    Zpin8.copy_(Zpin.to(torch.int8))
+    zptr8 = Zpin8.data_ptr()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     acc = torch.zeros(1, dtype=torch.float64, device="cuda")
 
@@ -237,6 +241,11 @@ def run_ours(args):
         tr = C.c_double()
         check(ctx.lib.kr_slq_trace(ctx.h, M.h, k, C.c_void_p(zptr), n, m, 0, C.byref(tr), None, None, None))
         return float(reduce_trace(tr.value).item())       # device -> host read of the step's result
+
+    def step_e2e_sign():
+        tr = C.c_double()
+        check(ctx.lib.kr_slq_trace_sign(ctx.h, M.h, k, C.c_void_p(zptr8), n, m, 0, C.byref(tr), None, None, None))
+        return float(reduce_trace(tr.value).item())
 
     def barrier():
         if world > 1:
@@ -309,6 +318,10 @@ def run_ours(args):
     ms_e2e, tr_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
     h1 = ctx.counters()
     e2e_steps = max(1, min(args.steps, 3))
+    step_e2e_sign()
+    g0 = ctx.counters()
+    ms_e2e8, tr_e2e8 = timed(step_e2e_sign, e2e_steps)
+    g1 = ctx.counters()
 
     if rank == 0:
         mv_step = k * m * world
@@ -345,6 +358,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": (h1["h2d_bytes"] - h0["h2d_bytes"]) // e2e_steps,
                     "d2h_bytes_per_step": (h1["d2h_bytes"] - h0["d2h_bytes"]) // e2e_steps + 8,
                     "ms_per_step": ms_e2e / e2e_steps, "trace_estimate": tr_e2e},
+            # same call path with the probes handed over as int8 signs (kr_slq_trace_sign): 1/8 of the upload
+            "e2e_sign_probes": {"value": mv_step * e2e_steps / (ms_e2e8 * 1e-3), "unit": UNIT,
+                                "h2d_bytes_per_step": (g1["h2d_bytes"] - g0["h2d_bytes"]) // e2e_steps,
+                                "ms_per_step": ms_e2e8 / e2e_steps, "trace_estimate": tr_e2e8},
             "gpu_launches": c1["launches"] - c0["launches"],
             "roofline": {"bound": "hbm", "kernel": "spmm_kernel<EpiDot> (CSR x 512-wide fp64 block + fused alpha dot)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -164,6 +164,10 @@ int  kr_mc_trace(kr_ctx* ctx, const kr_matrix* A, int op, double tol, int64_t ma
  * may be NULL. */
 int  kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, int64_t ldz,
                   int64_t m, int fun, double* tr, double* vals, double* alpha, double* beta);
+/* Same with Rademacher probes handed over as int8 signs (+1 / -1), column-major with leading dimension ldz:
+ * one eighth of the host -> device bytes, expanded to fp64 on the device; the arithmetic is unchanged. */
+int  kr_slq_trace_sign(kr_ctx* ctx, const kr_matrix* A, int64_t k, const signed char* Z, int64_t ldz,
+                       int64_t m, int fun, double* tr, double* vals, double* alpha, double* beta);
 int  kr_slq_trace_dev(kr_ctx* ctx, const kr_matrix* A, const kr_dense* Z, int64_t m, int fun,
                       double* tr, double* vals, double* alpha, double* beta);
 

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "kr_theta": [VP],
     "kr_mc_trace": [VP, VP, C.c_int, C.c_double, c_i64, VP, c_dp, c_dp, c_ip],
     "kr_slq_trace": [VP, VP, c_i64, VP, c_i64, c_i64, C.c_int, c_dp, VP, VP, VP],
+    "kr_slq_trace_sign": [VP, VP, c_i64, VP, c_i64, c_i64, C.c_int, c_dp, VP, VP, VP],
     "kr_slq_trace_dev": [VP, VP, VP, c_i64, C.c_int, c_dp, VP, VP, VP],
 }
 _RESTYPE = {"kr_last_error": C.c_char_p, "kr_version": C.c_char_p, "kr_ctx_destroy": None,

@@ -330,8 +330,12 @@ int kr_slq_trace_dev(kr_ctx* ctx, const kr_matrix* A, const kr_dense* Z, int64_t
     });
 }
 
-int kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, int64_t ldz, int64_t m, int fun,
-                 double* tr, double* vals, double* alpha, double* beta) {
+}  // extern "C"
+
+// Host-buffer SLQ pipeline shared by kr_slq_trace (fp64 probes) and kr_slq_trace_sign (int8 sign probes).
+template <class T>
+static int slq_trace_host(kr_ctx* ctx, const kr_matrix* A, int64_t k, const T* Z, int64_t ldz, int64_t m, int fun,
+                          double* tr, double* vals, double* alpha, double* beta) {
     return guarded([&] {
         if (!ctx || !A || !Z) fail(KR_ERR_ARG, "kr_slq_trace: null argument");
         if (fun < 0 || fun > 2) fail(KR_ERR_ARG, "unsupported function selector");
@@ -354,19 +358,19 @@ int kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, in
         const int64_t nch = (int64_t)cstart.size();
         if (!ctx->copy_stream) KR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         std::vector<std::unique_ptr<PanelBuf>> W(nch);
-        std::vector<std::unique_ptr<DevBuf<double>>> stage(nch);
+        std::vector<std::unique_ptr<DevBuf<T>>> stage(nch);
         std::vector<cudaEvent_t> ready(nch, nullptr);
         for (int64_t c = 0; c < nch; ++c) {
             W[c].reset(new PanelBuf(ctx, n, (int)cwidth[c]));
-            stage[c].reset(new DevBuf<double>(ctx, (size_t)std::max<int64_t>(n * cwidth[c], 1)));
+            stage[c].reset(new DevBuf<T>(ctx, (size_t)std::max<int64_t>(n * cwidth[c], 1)));
         }
         KR_CUDA(cudaStreamSynchronize(ctx->stream));     // pool buffers may still be in use by earlier work
         auto issue_copy = [&](int64_t c) {
             const int64_t c0 = cstart[c], cw = cwidth[c];
             if (n > 0 && cw > 0) {
-                KR_CUDA(cudaMemcpy2DAsync(stage[c]->p, n * sizeof(double), Z + c0 * ldz, ldz * sizeof(double),
-                                          n * sizeof(double), cw, cudaMemcpyHostToDevice, ctx->copy_stream));
-                ctx->counters[3] += n * cw * (int64_t)sizeof(double);
+                KR_CUDA(cudaMemcpy2DAsync(stage[c]->p, n * sizeof(T), Z + c0 * ldz, ldz * sizeof(T),
+                                          n * sizeof(T), cw, cudaMemcpyHostToDevice, ctx->copy_stream));
+                ctx->counters[3] += n * cw * (int64_t)sizeof(T);
             }
             cm_to_panel(ctx, stage[c]->p, n, *W[c], ctx->copy_stream);
             KR_CUDA(cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming));
@@ -406,15 +410,27 @@ int kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, in
         }
         KR_CUDA(cudaStreamSynchronize(ctx->copy_stream));
         for (auto e : ready) if (e) cudaEventDestroy(e);
-        SlqResult T;
-        T.vals = all_vals;
-        T.alpha = all_a;
-        T.beta = all_b;
+        SlqResult R;
+        R.vals = all_vals;
+        R.alpha = all_a;
+        R.beta = all_b;
         double s = 0.0;
         for (int64_t q = 0; q < k; ++q) s += all_vals[(size_t)q];
-        T.tr = k ? s / (double)k : 0.0;
-        slq_finish(T, m, tr, vals, alpha, beta);
+        R.tr = k ? s / (double)k : 0.0;
+        slq_finish(R, m, tr, vals, alpha, beta);
     });
+}
+
+extern "C" {
+
+int kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, int64_t ldz, int64_t m, int fun,
+                 double* tr, double* vals, double* alpha, double* beta) {
+    return slq_trace_host<double>(ctx, A, k, Z, ldz, m, fun, tr, vals, alpha, beta);
+}
+
+int kr_slq_trace_sign(kr_ctx* ctx, const kr_matrix* A, int64_t k, const signed char* Z, int64_t ldz, int64_t m, int fun,
+                      double* tr, double* vals, double* alpha, double* beta) {
+    return slq_trace_host<signed char>(ctx, A, k, Z, ldz, m, fun, tr, vals, alpha, beta);
 }
 
 int kr_theta(double theta[100]) {

@@ -66,6 +66,35 @@ panel_to_cm_kernel(const double* __restrict__ src, int64_t n, int cols, double* 
     }
 }
 
+// column-major int8 signs (+1 / -1, anything else is taken by its sign, 0 stays 0) -> panel-major fp64:
+// Rademacher probes carry one bit per entry, so the host -> device copy of kr_slq_trace_sign moves 1/8 of
+// the bytes of the fp64 entry point.
+__global__ void __launch_bounds__(256)
+cm_i8_to_panel_kernel(const signed char* __restrict__ src, int64_t ld, int64_t n, int cols,
+                      double* __restrict__ dst) {
+    __shared__ signed char t[PW][64 + 4];
+    const int q = blockIdx.y;
+    const int64_t r0 = (int64_t)blockIdx.x * 64;
+    for (int e = threadIdx.x; e < PW * 64; e += 256) {
+        int c = e / 64, i = e % 64;
+        int64_t r = r0 + i;
+        int col = q * PW + c;
+        t[c][i] = (r < n && col < cols) ? src[r + (int64_t)col * ld] : (signed char)0;
+    }
+    __syncthreads();
+    double* d = dst + (int64_t)q * n * PW + r0 * PW;
+    for (int e = threadIdx.x; e < PW * 64; e += 256) {
+        int i = e / PW, c = e % PW;
+        const int v = t[c][i];
+        if (r0 + i < n) d[e] = v > 0 ? 1.0 : (v < 0 ? -1.0 : 0.0);
+    }
+}
+inline void cm_to_panel(kr_ctx* ctx, const signed char* src_dev, int64_t ld, PanelBuf& dst, cudaStream_t stream = nullptr) {
+    if (dst.n == 0 || dst.panels == 0) return;
+    dim3 grid((unsigned)ceil_div(dst.n, 64), (unsigned)dst.panels);
+    cm_i8_to_panel_kernel<<<grid, 256, 0, stream ? stream : ctx->stream>>>(src_dev, ld, dst.n, dst.cols, dst.p());
+    check_launch(ctx, "cm_i8_to_panel_kernel");
+}
 inline void cm_to_panel(kr_ctx* ctx, const double* src_dev, int64_t ld, PanelBuf& dst, cudaStream_t stream = nullptr) {
     if (dst.n == 0 || dst.panels == 0) return;
     dim3 grid((unsigned)ceil_div(dst.n, 64), (unsigned)dst.panels);

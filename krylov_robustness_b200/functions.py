@@ -35,8 +35,16 @@ def slq_trace(A, Z, m=30, fun="exp", return_details=False):
     M = _mat(A)
     lib, ctx = M.ctx.lib, M.ctx
     tr = C.c_double()
+    sign = False
     if isinstance(Z, Dense):
         k = Z.k
+    elif isinstance(Z, np.ndarray) and Z.dtype == np.int8:
+        # Rademacher probes as int8 signs: 1/8 of the upload, expanded to fp64 on the device
+        sign = True
+        Z = Z if Z.ndim == 2 else Z[:, None]
+        if not (Z.strides[0] == 1 and Z.strides[1] >= max(Z.shape[0], 1)):      # column-major with any ld is taken as is
+            Z = np.asfortranarray(Z)
+        ldz, k = (Z.strides[1] if Z.shape[1] > 1 else max(Z.shape[0], 1)), Z.shape[1]
     else:
         Z, ldz = _f64_cm(Z)
         k = Z.shape[1]
@@ -46,8 +54,8 @@ def slq_trace(A, Z, m=30, fun="exp", return_details=False):
     if isinstance(Z, Dense):
         check(lib.kr_slq_trace_dev(ctx.h, M.h, Z.h, m, fun_id(fun), C.byref(tr), _ptr(vals), _ptr(al), _ptr(be)))
     else:
-        check(lib.kr_slq_trace(ctx.h, M.h, k, _ptr(Z), ldz, m, fun_id(fun), C.byref(tr), _ptr(vals), _ptr(al),
-                               _ptr(be)))
+        entry = lib.kr_slq_trace_sign if sign else lib.kr_slq_trace
+        check(entry(ctx.h, M.h, k, _ptr(Z), ldz, m, fun_id(fun), C.byref(tr), _ptr(vals), _ptr(al), _ptr(be)))
     if return_details:
         return tr.value, vals, al, be
     return tr.value

@@ -81,6 +81,12 @@ def test_slq_matches_oracle(kr, graphs, gname, fun):
     D = kr.Dense(n, 24).upload(Z)
     assert kr.slq_trace(kr.Matrix(A), D, 20, fun) == tr
     assert kr.slq_trace(kr.Matrix(A), D, 20, fun) == tr      # bit-reproducible run to run
+    # int8 sign probes (kr_slq_trace_sign): 1/8 of the upload, same fp64 arithmetic, identical result;
+    # a ragged leading dimension exercises the strided copy
+    Zs = np.zeros((n + 5, 24), dtype=np.int8, order="F")
+    Zs[:n] = Z.astype(np.int8)
+    tr8, vals8, _, _ = kr.slq_trace(A, Zs[:n], 20, fun, return_details=True)
+    assert tr8 == tr and np.array_equal(vals8, vals)
 
 
 def test_slq_power_law_64_probes(kr):
