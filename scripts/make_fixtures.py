@@ -21,8 +21,9 @@ def save(name, A):
     A.sort_indices()
     A.eliminate_zeros()
     assert (A != A.T).nnz == 0
-    np.savez_compressed(os.path.join(OUT, "graph_%s.npz" % name), n=A.shape[0], indptr=A.indptr.astype(np.int64),
-                        indices=A.indices.astype(np.int64), data=A.data)
+    idt = np.int32 if A.shape[0] > 50000 else np.int64          # loaders cast back; keeps the big fixture small
+    np.savez_compressed(os.path.join(OUT, "graph_%s.npz" % name), n=A.shape[0], indptr=A.indptr.astype(idt),
+                        indices=A.indices.astype(idt), data=A.data)
     print(name, A.shape[0], A.nnz)
 
 
@@ -47,7 +48,7 @@ def main():
     m = sio.loadmat(os.path.join(REF, "MIOBI Codes", "dt_oregon.mat"), spmatrix=True)
     for k in ("A0", "A1", "A8"):
         save("oregon_%s" % k, m[k])
-    for k in ("Anaheim", "Barcelona", "Rome"):
+    for k in ("Anaheim", "Barcelona", "Rome", "Vermont"):       # Vermont = the largest road network (config C2 at full size)
         p = sio.loadmat(os.path.join(REF, "datasets_paper", "Transport", k + ".mat"), spmatrix=True)
         save("transport_%s" % k, unweighted(p["Problem"]["A"][0, 0]))
     v = sio.loadmat(os.path.join(REF, "datasets_paper", "voltage_adjacencies_average_2.mat"), spmatrix=True)
