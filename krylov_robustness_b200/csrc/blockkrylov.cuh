@@ -9,6 +9,7 @@
 // step).  The small projected matrices (H, K, Cm, Gm) live on the host; their eigen-solves run on
 // the device (Jacobi kernel for n <= 110, cuSOLVER syevd above).
 #pragma once
+#include <chrono>
 #include <memory>
 
 #include "dense.cuh"
@@ -197,16 +198,54 @@ inline double fro_norm(const HostMat& R) {
     return std::sqrt(s);
 }
 
+// ---- host-side phase timers of the wide-block path (KR_PROFILE_WIDE=1 prints them to stderr at the end of
+// fun_update / trace_fun_update; they synchronise the stream, so they are a diagnostic, not a product path)
+struct WideProf {
+    bool on = getenv("KR_PROFILE_WIDE") != nullptr;
+    double eig_small = 0, eig_large = 0, step = 0, other = 0;
+    int n_small = 0, n_large = 0, n_step = 0, max_dim = 0;
+    static double now() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+    void report(const char* what) {
+        if (!on) return;
+        fprintf(stderr, "[kr wide] %s: krylov steps %d %.2f ms | eig(n<=110, smem Jacobi) %d %.2f ms | eig(syevd) %d %.2f ms "
+                        "(largest n %d)\n", what, n_step, step, n_small, eig_small, n_large, eig_large, max_dim);
+        eig_small = eig_large = step = other = 0;
+        n_small = n_large = n_step = max_dim = 0;
+    }
+};
+inline WideProf& wide_prof() { static WideProf p; return p; }
+
+inline int jacobi_max_dim() {
+    static const int v = [] { const char* e = getenv("KR_JACOBI_MAX"); return e ? atoi(e) : 16; }();
+    return v;
+}
+
 // ---- small symmetric eigen-solves on the device (host in / host out)
 // evals (ascending); if F != nullptr also F = V f(D) V'.
 inline void sym_eig_dev(kr_ctx* ctx, const HostMat& S, std::vector<double>& evals, int fun, HostMat* F) {
     const int n = (int)S.rows;
     evals.assign(n, 0.0);
     if (n == 0) return;
+    WideProf& wp = wide_prof();
+    const double t_begin = wp.on ? WideProf::now() : 0.0;
+    struct Scope {
+        WideProf& wp; double t0; int n; bool small;
+        ~Scope() {
+            if (!wp.on) return;
+            const double dt = WideProf::now() - t0;
+            if (small) { wp.eig_small += dt; wp.n_small++; } else { wp.eig_large += dt; wp.n_large++; }
+            wp.max_dim = std::max(wp.max_dim, n);
+        }
+    } scope{wp, t_begin, n, n <= jacobi_max_dim()};
     DevBuf<double> dA(ctx, (size_t)n * n), dW(ctx, n);
     dA.upload(S.a.data(), (size_t)n * n);
     const bool vec = F != nullptr;
-    if (jacobi_smem_bytes(n, vec) <= JAC_SMEM_LIMIT) {
+    // One-CTA cyclic Jacobi only for tiny projections: measured 12-15 ms per solve at n = 100-156 against
+    // 1.7 ms for cuSOLVER syevd at n = 208 (profiles/r01_wide_block_phases.txt); it wins only below ~16-32, where
+    // syevd's fixed cost of several launches dominates.
+    if (n <= jacobi_max_dim() && jacobi_smem_bytes(n, vec) <= JAC_SMEM_LIMIT) {
         if (!vec) {
             static bool set1 = false;
             if (!set1) { KR_CUDA(cudaFuncSetAttribute(eigvals_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_LIMIT)); set1 = true; }
@@ -464,7 +503,9 @@ inline TfuResult trace_fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64
             st = krylov_start(ctx, M, false, rk, std::move(b0));
             Cm = core_Cm(ctx, st.get(), Ud, B);
         } else {
+            const double t0 = wide_prof().on ? WideProf::now() : 0.0;
             krylov_step(st.get());
+            if (wide_prof().on) { KR_CUDA(cudaStreamSynchronize(ctx->stream)); wide_prof().step += WideProf::now() - t0; wide_prof().n_step++; }
         }
         const int64_t nn = st->H.rows - rk;
         HostMat G(nn, nn), tG(nn, nn);
@@ -489,6 +530,7 @@ inline TfuResult trace_fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64
         if (done || st->lucky) break;
     }
     out.iter = std::min(j, it);
+    wide_prof().report("trace_fun_update");
     return out;
 }
 
@@ -527,7 +569,9 @@ inline FuInfo fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64_t rk, co
             st = krylov_start(ctx, M, want_basis, rk, std::move(b0));
             Cm = core_Cm(ctx, st.get(), Ud, B);
         } else {
+            const double t0 = wide_prof().on ? WideProf::now() : 0.0;
             krylov_step(st.get());
+            if (wide_prof().on) { KR_CUDA(cudaStreamSynchronize(ctx->stream)); wide_prof().step += WideProf::now() - t0; wide_prof().n_step++; }
         }
         if (want_basis && 2 * st->vcols >= n) {     // :85-90 dense fallback
             HostMat fA = dense_of(M), fAt = fA;
@@ -599,6 +643,7 @@ inline FuInfo fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64_t rk, co
     res.Um.buf.zero();
     KR_CUDA(cudaMemcpyAsync(res.Um.p(), st->V.p(), (size_t)n * keep * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     KR_CUDA(cudaStreamSynchronize(ctx->stream));
+    wide_prof().report("fun_update");
     return info;
 }
 
