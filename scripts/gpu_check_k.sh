@@ -1,11 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_spmm.py -m gpu -q --timeout=600 -k "slq" > gpurun_out/pytest_sign.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_sign.log; tail -5 gpurun_out/pytest_sign.log; grep "^E " gpurun_out/pytest_sign.log | head
-KR_BENCH_EDGES=0 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_sign.log 2>&1
+timeout 900 python scripts/replay_weighted.py --graphs grid_England,grid_Mexico --oracle > gpurun_out/replay_weighted3.jsonl 2> gpurun_out/replay_weighted3.err
 python - <<PY
 import json
-l=[x for x in open('gpurun_out/bench_sign.log') if x.startswith('{')]
-d=json.loads(l[-1]); print('value',d['value'],'ms/step',d['ms_per_step'],'e2e',d['e2e']['value'],'e2e ms',d['e2e']['ms_per_step'],'sign',d['e2e_sign_probes'])
+for l in open('gpurun_out/replay_weighted3.jsonl'):
+    d=json.loads(l)
+    if 'compare' in d: print(d['graph'], d['method'], 'same_edges', d['same_edges'], 'rel_fval_diff %.1e'%d['rel_fval_diff'], 'speedup run %.2f per-callback %.2f'%(d['speedup_whole_run'], d['speedup_per_callback']))
+    else: print('   ', d['impl'], 'time %.2f'%d['time_s'], 'callbacks', d['callbacks'], 'ms/callback %.1f'%d['ms_per_callback'])
 PY
-tail -3 gpurun_out/bench_sign.log | cut -c1-300
-python scripts/time_set_edges.py 2>&1 | tail -2
+tail -3 gpurun_out/replay_weighted3.err
