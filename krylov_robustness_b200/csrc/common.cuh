@@ -213,8 +213,10 @@ inline void* kr_ctx::alloc(size_t bytes) {
 
 inline void kr_ctx::release(void* p, size_t bytes) {
     size_t b = kr::bucket(bytes);
-    // keep at most 48 GiB cached; large one-off buffers go straight back to the driver
-    if (pool_bytes + b > (size_t(48) << 30)) {
+    // keep at most 96 GiB cached (a B200 has 180 GB; the candidate-pair path cycles three ~17 GB blocks per
+    // chunk and must not pay cudaFree + cudaMalloc for one of them on every chunk); larger one-off buffers go
+    // straight back to the driver.  alloc() trims the pool and retries when the driver runs out.
+    if (pool_bytes + b > (size_t(96) << 30)) {
         cudaStreamSynchronize(stream);
         cudaFree(p);
         return;

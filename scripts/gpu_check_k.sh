@@ -1,11 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python scripts/replay_weighted.py --graphs grid_England,grid_Mexico --oracle > gpurun_out/replay_weighted3.jsonl 2> gpurun_out/replay_weighted3.err
-python - <<PY
-import json
-for l in open('gpurun_out/replay_weighted3.jsonl'):
-    d=json.loads(l)
-    if 'compare' in d: print(d['graph'], d['method'], 'same_edges', d['same_edges'], 'rel_fval_diff %.1e'%d['rel_fval_diff'], 'speedup run %.2f per-callback %.2f'%(d['speedup_whole_run'], d['speedup_per_callback']))
-    else: print('   ', d['impl'], 'time %.2f'%d['time_s'], 'callbacks', d['callbacks'], 'ms/callback %.1f'%d['ms_per_callback'])
-PY
-tail -3 gpurun_out/replay_weighted3.err
+for v in pool48 pool96; do
+  lib=krylov_robustness_b200/libkrylov_b200.so
+  [ $v == pool48 ] && lib=krylov_robustness_b200/libkrylov_b200_pool48.so
+  KR_B200_LIB=$PWD/$lib timeout 600 python scripts/bench_edges.py --ncand 6000 > gpurun_out/bench_edges_$v.json 2> gpurun_out/bench_edges_$v.err; echo "$v rc $?"; cut -c1-330 gpurun_out/bench_edges_$v.json; tail -2 gpurun_out/bench_edges_$v.err
+done
