@@ -95,3 +95,13 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_numa_binding_is_a_noop_without_topology():
+    """bind_to_gpu_numa_node must never raise: no GPU / no sysfs topology -> None and the affinity is untouched."""
+    import os
+    from krylov_robustness_b200.parallel import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), dict)
+    if not os.path.exists("/dev/nvidia0"):
+        assert os.sched_getaffinity(0) == before
