@@ -14,6 +14,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    # The library is a build artefact (git-ignored).  On a fresh checkout with a CUDA toolkit, compile it once
+    # (nvcc cross-compiles sm_100a without a GPU, ~1.5 min) so that the C-ABI / MEX-gateway tests have
+    # something to load; on the GPU box the prebuilt .so travels with the snapshot.
+    lib = os.path.join(ROOT, "krylov_robustness_b200", "libkrylov_b200.so")
+    if not os.path.exists(lib) and os.path.exists("/usr/local/cuda/bin/nvcc"):
+        import subprocess
+        subprocess.run(["bash", os.path.join(ROOT, "krylov_robustness_b200", "csrc", "build.sh")], check=False)
     warnings.filterwarnings("ignore", message=".*Reached maximum number of iterations.*")
     warnings.filterwarnings("ignore", message=".*lucky breakdown.*")
 
