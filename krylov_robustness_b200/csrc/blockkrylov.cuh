@@ -217,6 +217,16 @@ struct WideProf {
 };
 inline WideProf& wide_prof() { static WideProf p; return p; }
 
+// Vf(:, k) = V(:, k) * f(w_k)  (column-major n x n), the first half of F = V f(D) V'
+__global__ void scale_cols_fun_kernel(const double* __restrict__ V, const double* __restrict__ w, int n, int fun,
+                                      double* __restrict__ Vf) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * n) return;
+    const double x = w[e / n];
+    const double fx = fun == KR_FUN_EXP ? exp(x) : fun == KR_FUN_SINH ? sinh(x) : cosh(x);
+    Vf[e] = V[e] * fx;
+}
+
 inline int jacobi_max_dim() {
     static const int v = [] { const char* e = getenv("KR_JACOBI_MAX"); return e ? atoi(e) : 16; }();
     return v;
@@ -269,20 +279,16 @@ inline void sym_eig_dev(kr_ctx* ctx, const HostMat& S, std::vector<double>& eval
     DevBuf<int> info(ctx, 1);
     KR_CUSOLVER(cusolverDnDsyevd(ctx->cusolver, jobz, CUBLAS_FILL_MODE_LOWER, n, dA.p, n, dW.p, work.p, lwork, info.p));
     ctx->counters[0] += 1;
-    evals = dW.to_host();
     if (vec) {
-        std::vector<double> V((size_t)n * n);
-        dA.download(V.data(), (size_t)n * n);
-        std::vector<double> Vf((size_t)n * n);
-        for (int k = 0; k < n; ++k) {
-            double fk = fun == KR_FUN_EXP ? std::exp(evals[k]) : fun == KR_FUN_SINH ? std::sinh(evals[k]) : std::cosh(evals[k]);
-            for (int i = 0; i < n; ++i) Vf[(size_t)i + (size_t)k * n] = V[(size_t)i + (size_t)k * n] * fk;
-        }
+        // F = (V f(D)) V' entirely on the device: one column-scaling kernel + one dgemm, one download
         DevBuf<double> dVf(ctx, (size_t)n * n), dF(ctx, (size_t)n * n);
-        dVf.upload(Vf.data(), (size_t)n * n);
+        KR_LAUNCH(ctx, scale_cols_fun_kernel, (int)ceil_div((int64_t)n * n, 256), 256, 0, dA.p, dW.p, n, fun, dVf.p);
         gemm(ctx, false, true, n, n, n, 1.0, dVf.p, n, dA.p, n, 0.0, dF.p, n);
         *F = HostMat(n, n);
+        KR_CUDA(cudaMemcpyAsync(evals.data(), dW.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         dF.download(F->a.data(), (size_t)n * n);
+    } else {
+        evals = dW.to_host();
     }
 }
 
@@ -375,7 +381,13 @@ inline void krylov_step(kr_krylov* st) {
                     for (int64_t k = 0; k < bs; ++k) s += Rf(k, i) * Rf(k, j);
                     RtR(i, j) = s;
                 }
-            st->lucky = (bs == 1 ? std::abs(Rf(0, 0)) : std::sqrt(sym_norm2_dev(ctx, RtR))) < 1e-12;
+            // ||R||_F / sqrt(bs) <= ||R||_2 <= ||R||_F: away from breakdown the Frobenius norm already decides
+            // and the bs x bs eigen-solve (one more device round trip per step) is skipped
+            const double fro = fro_norm(Rf);
+            if (bs == 1) st->lucky = std::abs(Rf(0, 0)) < 1e-12;
+            else if (fro / std::sqrt((double)bs) >= 1e-12) st->lucky = false;
+            else if (fro < 1e-12) st->lucky = true;
+            else st->lucky = std::sqrt(sym_norm2_dev(ctx, RtR)) < 1e-12;
         }
         // third reorthogonalisation (:104-106)
         DevBuf<double> dhh(ctx, (size_t)c * bs);

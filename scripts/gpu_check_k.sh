@@ -1,7 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in pool48 pool96; do
-  lib=krylov_robustness_b200/libkrylov_b200.so
-  [ $v == pool48 ] && lib=krylov_robustness_b200/libkrylov_b200_pool48.so
-  KR_B200_LIB=$PWD/$lib timeout 600 python scripts/bench_edges.py --ncand 6000 > gpurun_out/bench_edges_$v.json 2> gpurun_out/bench_edges_$v.err; echo "$v rc $?"; cut -c1-330 gpurun_out/bench_edges_$v.json; tail -2 gpurun_out/bench_edges_$v.err
-done
+python -m pytest tests -m gpu -q --timeout=900 > gpurun_out/pytest_k5.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_k5.log; tail -4 gpurun_out/pytest_k5.log; grep "^E " gpurun_out/pytest_k5.log | head
+./scripts/gpu_prof_wide.sh 2>&1 | grep "total ms\|====\|kr wide" | tail -6
