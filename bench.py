@@ -125,7 +125,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(1),
+            "config": config_dict(max(int(args.gpus), 1)),      # the arm's config at this N (the CPU rate does not scale with N)
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference is MATLAB-only (no MATLAB/Octave in the image): this is the NumPy/SciPy "
