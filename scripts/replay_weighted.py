@@ -89,16 +89,39 @@ def run(P, A, fun, method, args):
                 f, g = P.fun_and_grad_krylov_fun(x, A, E, fun, df, dfA, tol, args.it)
         return float(f), np.asarray(g, dtype=np.float64)
 
-    res = so.minimize(fg, np.zeros(len(E)), jac=True, method="SLSQP", bounds=list(zip(LB, UB)),
-                      constraints=[{"type": "ineq", "fun": lambda x: args.weight - x.sum(),
-                                    "jac": lambda x: -np.ones_like(x)}],
-                      options={"maxiter": args.maxiter, "ftol": 1e-9})
+    hcalls = [0]
+    if args.hessian:
+        # Tests/test_weighted_sinh_hessian.m:189-208: the same problem with the exact Hessian callback
+        # hessianfcn_fun / hessianfcn_exp (pairwise Frechet derivatives); SciPy's trust-constr takes its part
+        def hess(x):
+            hcalls[0] += 1
+            tc = time.perf_counter()
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    if fun == "exp":
+                        return np.asarray(P.hessianfcn_exp(x, A, E, tol, args.it))
+                    return np.asarray(P.hessianfcn_fun(x, A, E, df, tol, args.it))
+            finally:
+                cb_time[0] += time.perf_counter() - tc
+
+        # interior-point methods start strictly inside the box (fmincon shifts x0 = 0 the same way)
+        x0 = np.clip(np.zeros(len(E)), LB + 1e-2 * (UB - LB), UB - 1e-2 * (UB - LB))
+        res = so.minimize(fg, x0, jac=True, hess=hess, method="trust-constr",
+                          bounds=so.Bounds(LB, UB, keep_feasible=True),
+                          constraints=[so.LinearConstraint(np.ones((1, len(E))), -np.inf, args.weight)],
+                          options={"maxiter": args.maxiter, "gtol": 1e-3, "xtol": 1e-8})
+    else:
+        res = so.minimize(fg, np.zeros(len(E)), jac=True, method="SLSQP", bounds=list(zip(LB, UB)),
+                          constraints=[{"type": "ineq", "fun": lambda x: args.weight - x.sum(),
+                                        "jac": lambda x: -np.ones_like(x)}],
+                          options={"maxiter": args.maxiter, "ftol": 1e-9})
     dt = time.perf_counter() - t0
     lam = np.linalg.eigvalsh(A.toarray())
     trfA = float(np.sum(getattr(np, fun)(lam)))
     return {"n": n, "method": method, "fun": fun, "edges": E.tolist(), "x": res.x.tolist(), "fval": float(res.fun),
-            "rel_gain": float(-res.fun / trfA), "iterations": int(res.nit), "callbacks": calls[0], "time_s": dt, "callback_s": cb_time[0],
-            "ms_per_callback": 1e3 * cb_time[0] / max(calls[0], 1)}
+            "rel_gain": float(-res.fun / trfA), "iterations": int(res.nit), "callbacks": calls[0], "hessian_callbacks": hcalls[0], "time_s": dt,
+            "callback_s": cb_time[0], "ms_per_callback": 1e3 * cb_time[0] / max(calls[0] + hcalls[0], 1)}
 
 
 def main():
@@ -113,6 +136,7 @@ def main():
     ap.add_argument("--it", type=int, default=100)
     ap.add_argument("--maxiter", type=int, default=200)       # (:26)
     ap.add_argument("--oracle", action="store_true")
+    ap.add_argument("--hessian", action="store_true", help="exact-Hessian variant (Tests/test_weighted_*_hessian.m)")
     args = ap.parse_args()
     import krylov_robustness_b200 as kr
     from conftest import load_graph
