@@ -132,14 +132,17 @@ int kr_matrix_create(kr_ctx* ctx, int64_t n, int64_t nnz, const int64_t* row_ptr
         M->host.n = n;
         M->host.row_ptr.assign(row_ptr, row_ptr + n + 1);
         M->host.col.resize(nnz);
-        M->host.val.assign(val, val + nnz);
+        M->host.val.resize(nnz);
         for (int64_t i = 0; i < n; ++i)
             if (row_ptr[i + 1] < row_ptr[i]) fail(KR_ERR_ARG, "kr_matrix_create: row_ptr not monotone");
+        int bad = 0;
+#pragma omp parallel for reduction(|| : bad) schedule(static)
         for (int64_t p = 0; p < nnz; ++p) {
-            if (col_idx[p] < 0 || col_idx[p] >= n)
-                fail(KR_ERR_ARG, "kr_matrix_create: column index out of range (The matrix A should be square)");
+            bad = bad || col_idx[p] < 0 || col_idx[p] >= n;
             M->host.col[p] = (int32_t)col_idx[p];
+            M->host.val[p] = val[p];
         }
+        if (bad) fail(KR_ERR_ARG, "kr_matrix_create: column index out of range (The matrix A should be square)");
         analyse_and_upload(M.get());
         *out = M.release();
     });
@@ -177,27 +180,40 @@ int kr_matrix_set_edges(kr_matrix* A, int64_t count, const int64_t* ii, const in
             edits[i][(int32_t)j] = v[e];
             edits[j][(int32_t)i] = v[e];
         }
+        // rebuild only the touched rows, then copy the untouched ones in parallel into their new places
+        std::map<int64_t, std::vector<std::pair<int32_t, double>>> rebuilt;
+        for (auto& ed : edits) {
+            const int64_t i = ed.first;
+            std::map<int32_t, double> row;
+            for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) row[H.col[p]] = H.val[p];
+            for (auto& kv : ed.second) row[kv.first] = kv.second;
+            auto& out = rebuilt[i];
+            for (auto& kv : row)
+                if (kv.second != 0.0) out.emplace_back(kv.first, kv.second);   // MATLAB sparse assignment of 0 removes the entry
+        }
         CsrHost N;
         N.n = n;
         N.row_ptr.assign(n + 1, 0);
-        N.col.reserve(H.col.size() + 2 * count);
-        N.val.reserve(H.val.size() + 2 * count);
-        for (int64_t i = 0; i < n; ++i) {
-            auto it = edits.find(i);
-            if (it == edits.end()) {
-                N.col.insert(N.col.end(), H.col.begin() + H.row_ptr[i], H.col.begin() + H.row_ptr[i + 1]);
-                N.val.insert(N.val.end(), H.val.begin() + H.row_ptr[i], H.val.begin() + H.row_ptr[i + 1]);
-            } else {
-                std::map<int32_t, double> row;
-                for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) row[H.col[p]] = H.val[p];
-                for (auto& kv : it->second) row[kv.first] = kv.second;
-                for (auto& kv : row)
-                    if (kv.second != 0.0) {           // MATLAB sparse assignment of 0 removes the entry
-                        N.col.push_back(kv.first);
-                        N.val.push_back(kv.second);
-                    }
+        {
+            auto it = rebuilt.begin();
+            for (int64_t i = 0; i < n; ++i) {
+                int64_t len = H.row_ptr[i + 1] - H.row_ptr[i];
+                if (it != rebuilt.end() && it->first == i) { len = (int64_t)it->second.size(); ++it; }
+                N.row_ptr[i + 1] = N.row_ptr[i] + len;
             }
-            N.row_ptr[i + 1] = (int64_t)N.col.size();
+        }
+        N.col.resize((size_t)N.row_ptr[n]);
+        N.val.resize((size_t)N.row_ptr[n]);
+#pragma omp parallel for schedule(dynamic, 4096)
+        for (int64_t i = 0; i < n; ++i) {
+            auto it = rebuilt.find(i);
+            if (it == rebuilt.end()) {
+                std::copy(H.col.begin() + H.row_ptr[i], H.col.begin() + H.row_ptr[i + 1], N.col.begin() + N.row_ptr[i]);
+                std::copy(H.val.begin() + H.row_ptr[i], H.val.begin() + H.row_ptr[i + 1], N.val.begin() + N.row_ptr[i]);
+            } else {
+                int64_t w = N.row_ptr[i];
+                for (auto& kv : it->second) { N.col[(size_t)w] = kv.first; N.val[(size_t)w] = kv.second; ++w; }
+            }
         }
         H = std::move(N);
         analyse_and_upload(A, /*keep_symmetric=*/true);

@@ -98,10 +98,11 @@ inline CsrHost transpose(const CsrHost& A) {
 // Rows must have sorted, duplicate-free columns for the symmetry comparison to be exact.
 inline void canonicalize(CsrHost& A) {
     const int64_t n = A.n;
-    bool sorted = true;
-    for (int64_t i = 0; i < n && sorted; ++i)
+    int sorted = 1;
+#pragma omp parallel for reduction(&& : sorted) schedule(static)
+    for (int64_t i = 0; i < n; ++i)
         for (int64_t p = A.row_ptr[i] + 1; p < A.row_ptr[i + 1]; ++p)
-            if (A.col[p - 1] >= A.col[p]) { sorted = false; break; }
+            sorted = sorted && (A.col[p - 1] < A.col[p]);
     if (sorted) return;
     CsrHost T = transpose(A);      // two transposes = stable counting sort by column
     A = transpose(T);
@@ -121,71 +122,100 @@ inline void canonicalize(CsrHost& A) {
     A.val.resize(w);
 }
 
-inline void upload_csr(kr_ctx* ctx, const CsrHost& H, CsrDev& D) {
+// Host-side layout of the device CSR (everything upload_csr ships): rows in stored (length-sorted) order.
+struct PreparedCsr {
+    int64_t n = 0, nnz = 0;
+    bool uniform = false;
+    double uval = 1.0;
+    std::vector<int> srp, order;
+    std::vector<int32_t> scol;
+    std::vector<double> sval;
+    std::vector<RowTile> tiles;
+};
+
+inline int lane_class_of(int len) {
+    return len >= SPMM_LONG_ROW ? 6 : len >= 256 ? 3 : len >= 64 ? 2 : len >= 16 ? 1 : 0;
+}
+
+// Pure host work (no CUDA calls): value uniformity, the stable decreasing-length row order (a counting sort,
+// O(n + max length)), the re-packed index / value arrays (OpenMP over rows) and the tile list.
+inline PreparedCsr prepare_csr(const CsrHost& H) {
+    PreparedCsr P;
     const int64_t n = H.n, nnz = H.row_ptr[n];
     if (n >= (int64_t(1) << 31) - 64 || nnz >= (int64_t(1) << 31) - 64)
         fail(KR_ERR_UNSUPPORTED, "matrix too large for 32-bit device indices (n=%lld nnz=%lld)",
              (long long)n, (long long)nnz);
-    D.n = n;
-    D.nnz = nnz;
-    std::vector<int> rp(n + 1);
-    for (int64_t i = 0; i <= n; ++i) rp[i] = (int)H.row_ptr[i];
-    bool uniform = nnz > 0;
-    for (int64_t p = 1; p < nnz && uniform; ++p) uniform = (H.val[p] == H.val[0]);
-    D.pattern_only = uniform;
-    D.uval = uniform ? H.val[0] : 1.0;
-    // ---- stored order: decreasing length (stable)
-    std::vector<int> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return (rp[a + 1] - rp[a]) > (rp[b + 1] - rp[b]);
-    });
-    std::vector<int> srp(n + 1, 0);
-    std::vector<int32_t> scol((size_t)std::max<int64_t>(nnz, 1));
-    std::vector<double> sval(uniform ? 1 : (size_t)std::max<int64_t>(nnz, 1));
+    P.n = n;
+    P.nnz = nnz;
+    int uniform = nnz > 0;
+    const double v0 = nnz > 0 ? H.val[0] : 1.0;
+#pragma omp parallel for reduction(&& : uniform) schedule(static)
+    for (int64_t p = 0; p < nnz; ++p) uniform = uniform && (H.val[p] == v0);
+    P.uniform = uniform != 0;
+    P.uval = P.uniform ? v0 : 1.0;
+    // ---- stored order: decreasing length, stable in the row index
+    int maxlen = 0;
+    for (int64_t i = 0; i < n; ++i) maxlen = std::max(maxlen, (int)(H.row_ptr[i + 1] - H.row_ptr[i]));
+    std::vector<int64_t> start((size_t)maxlen + 2, 0);
+    for (int64_t i = 0; i < n; ++i) start[(size_t)(maxlen - (int)(H.row_ptr[i + 1] - H.row_ptr[i])) + 1]++;
+    for (size_t b = 1; b < start.size(); ++b) start[b] += start[b - 1];
+    P.order.resize(n);
+    for (int64_t i = 0; i < n; ++i) P.order[(size_t)start[(size_t)(maxlen - (int)(H.row_ptr[i + 1] - H.row_ptr[i]))]++] = (int)i;
+    P.srp.assign(n + 1, 0);
     for (int64_t s = 0; s < n; ++s) {
-        const int r = order[s];
-        const int len = rp[r + 1] - rp[r];
-        srp[s + 1] = srp[s] + len;
-        std::copy(H.col.begin() + rp[r], H.col.begin() + rp[r + 1], scol.begin() + srp[s]);
-        if (!uniform) std::copy(H.val.begin() + rp[r], H.val.begin() + rp[r + 1], sval.begin() + srp[s]);
+        const int r = P.order[s];
+        P.srp[s + 1] = P.srp[s] + (int)(H.row_ptr[r + 1] - H.row_ptr[r]);
     }
-    D.row_ptr.reset(ctx, n + 1);
-    D.row_ptr.upload(srp.data(), n + 1);
-    D.col.reset(ctx, std::max<int64_t>(nnz, 1));
-    if (nnz) D.col.upload(scol.data(), nnz);
-    if (!uniform) {
-        D.val.reset(ctx, std::max<int64_t>(nnz, 1));
-        if (nnz) D.val.upload(sval.data(), nnz);
-    } else {
-        D.val.free();
+    P.scol.resize((size_t)std::max<int64_t>(nnz, 1));
+    P.sval.resize(P.uniform ? 1 : (size_t)std::max<int64_t>(nnz, 1));
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t s = 0; s < n; ++s) {
+        const int r = P.order[s];
+        std::copy(H.col.begin() + H.row_ptr[r], H.col.begin() + H.row_ptr[r + 1], P.scol.begin() + P.srp[s]);
+        if (!P.uniform) std::copy(H.val.begin() + H.row_ptr[r], H.val.begin() + H.row_ptr[r + 1], P.sval.begin() + P.srp[s]);
     }
     // ---- tiles: runs of one lane class, nonzeros <= SPMM_CAP, rows <= SPMM_MAX_ROWS; long rows alone
-    auto lane_class = [](int len) {
-        return len >= SPMM_LONG_ROW ? 6 : len >= 256 ? 3 : len >= 64 ? 2 : len >= 16 ? 1 : 0;
-    };
-    std::vector<RowTile> tiles;
     int64_t i = 0;
     while (i < n) {
-        const int cls = lane_class(srp[i + 1] - srp[i]);
+        const int cls = lane_class_of(P.srp[i + 1] - P.srp[i]);
         int64_t j = i + 1;
         if (cls != 6) {
-            int64_t acc = srp[i + 1] - srp[i];
+            int64_t acc = P.srp[i + 1] - P.srp[i];
             while (j < n && j - i < SPMM_MAX_ROWS) {
-                const int len = srp[j + 1] - srp[j];
-                if (lane_class(len) != cls || acc + len > SPMM_CAP) break;
+                const int len = P.srp[j + 1] - P.srp[j];
+                if (lane_class_of(len) != cls || acc + len > SPMM_CAP) break;
                 acc += len;
                 ++j;
             }
         }
-        tiles.push_back(RowTile{(int)i, (int)(j - i), cls, 0});
+        P.tiles.push_back(RowTile{(int)i, (int)(j - i), cls, 0});
         i = j;
     }
-    D.ntiles = (int)tiles.size();
+    return P;
+}
+
+inline void upload_csr(kr_ctx* ctx, const CsrHost& H, CsrDev& D) {
+    const PreparedCsr P = prepare_csr(H);
+    const int64_t n = P.n, nnz = P.nnz;
+    D.n = n;
+    D.nnz = nnz;
+    D.pattern_only = P.uniform;
+    D.uval = P.uval;
+    D.row_ptr.reset(ctx, n + 1);
+    D.row_ptr.upload(P.srp.data(), n + 1);
+    D.col.reset(ctx, std::max<int64_t>(nnz, 1));
+    if (nnz) D.col.upload(P.scol.data(), nnz);
+    if (!P.uniform) {
+        D.val.reset(ctx, std::max<int64_t>(nnz, 1));
+        if (nnz) D.val.upload(P.sval.data(), nnz);
+    } else {
+        D.val.free();
+    }
+    D.ntiles = (int)P.tiles.size();
     D.row_order.reset(ctx, std::max<int64_t>(n, 1));
-    if (n) D.row_order.upload(order.data(), n);
-    D.tiles.reset(ctx, std::max<size_t>(tiles.size(), 1));
-    if (!tiles.empty()) D.tiles.upload(tiles.data(), tiles.size());
+    if (n) D.row_order.upload(P.order.data(), n);
+    D.tiles.reset(ctx, std::max<size_t>(P.tiles.size(), 1));
+    if (!P.tiles.empty()) D.tiles.upload(P.tiles.data(), P.tiles.size());
     KR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging vectors die here
 }
 
@@ -207,31 +237,53 @@ namespace kr {
 
 // keep_symmetric: the caller guarantees the edit preserved symmetry (kr_matrix_set_edges writes both
 // triangles), so the O(nnz) transpose + comparison is skipped and ||A||_1 is the max row abs-sum.
+// A == A' for a canonical (sorted, duplicate-free) CSR without building the transpose: walking the rows in
+// ascending order, the entries (j, i) of row j are met in ascending i, so a per-row cursor finds the partner of
+// every stored (i, j, v) in O(1) - the counting-sort transpose without its output arrays.
+inline bool is_symmetric_csr(const CsrHost& H) {
+    const int64_t n = H.n;
+    std::vector<int64_t> cur(H.row_ptr.begin(), H.row_ptr.end() - 1);
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) {
+            const int32_t j = H.col[p];
+            const int64_t q = cur[j];
+            if (q >= H.row_ptr[j + 1] || H.col[q] != (int32_t)i || H.val[q] != H.val[p]) return false;
+            cur[j] = q + 1;
+        }
+    return true;    // every row's cursor consumed exactly its entries (counts match because all nnz partners were found)
+}
+
 inline void analyse_and_upload(kr_matrix* M, bool keep_symmetric = false) {
     CsrHost& H = M->host;
     canonicalize(H);
     const int64_t n = H.n;
     CsrHost T;
-    if (keep_symmetric && M->symmetric) {
-        M->symmetric = true;
-    } else {
-        T = transpose(H);
-        M->symmetric = (T.row_ptr == H.row_ptr) && (T.col == H.col) && (T.val == H.val);
+    if (!(keep_symmetric && M->symmetric)) {
+        M->symmetric = is_symmetric_csr(H);
+        if (!M->symmetric) T = transpose(H);
     }
-    M->nonnegative = true;
-    M->trace = 0.0;
-    for (int64_t i = 0; i < n; ++i)
-        for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) {
-            if (H.val[p] < 0) M->nonnegative = false;
-            if (H.col[p] == i) M->trace += H.val[p];
-        }
+    int nonneg = 1;
+    double tr = 0.0, norm1 = 0.0;
     const CsrHost& C = M->symmetric ? H : T;       // column abs-sums of A = row abs-sums of A'
-    M->norm1 = 0.0;
+    // the trace feeds expmv's shift mu = trace / n: summed sequentially in row order (diagonal entry by binary
+    // search) so that it does not depend on the thread count
     for (int64_t i = 0; i < n; ++i) {
-        double s = 0;
-        for (int64_t p = C.row_ptr[i]; p < C.row_ptr[i + 1]; ++p) s += std::abs(C.val[p]);
-        M->norm1 = std::max(M->norm1, s);
+        const int32_t* b = H.col.data() + H.row_ptr[i];
+        const int32_t* e = H.col.data() + H.row_ptr[i + 1];
+        const int32_t* q = std::lower_bound(b, e, (int32_t)i);
+        if (q != e && *q == (int32_t)i) tr += H.val[(size_t)(q - H.col.data())];
     }
+#pragma omp parallel for reduction(&& : nonneg) reduction(max : norm1) schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p)
+            if (H.val[p] < 0) nonneg = 0;
+        double sabs = 0;
+        for (int64_t p = C.row_ptr[i]; p < C.row_ptr[i + 1]; ++p) sabs += std::abs(C.val[p]);
+        norm1 = std::max(norm1, sabs);
+    }
+    M->nonnegative = nonneg != 0;
+    M->trace = tr;
+    M->norm1 = norm1;
     upload_csr(M->ctx, H, M->dev);
     if (!M->symmetric) upload_csr(M->ctx, T, M->devT);
     else { M->devT = CsrDev(); }

@@ -1,3 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_replay.py -m gpu -q --timeout=900 > gpurun_out/pytest_replay.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_replay.log; tail -5 gpurun_out/pytest_replay.log; grep "^E " gpurun_out/pytest_replay.log | head
+python scripts/time_set_edges.py 2>&1 | tail -1
+OMP_NUM_THREADS=1 python scripts/time_set_edges.py 2>&1 | tail -1
+python -m pytest tests -m gpu -q --timeout=900 > gpurun_out/pytest_k6.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_k6.log; tail -4 gpurun_out/pytest_k6.log; grep "^E " gpurun_out/pytest_k6.log | head
