@@ -7,12 +7,15 @@ Each fixture is a CSR triple (indptr, indices, data) + n in one .npz (a few kB e
 """
 import os
 
+import sys
+
 import numpy as np
 import scipy.io as sio
 import scipy.sparse as sp
 from scipy.sparse.csgraph import connected_components
 
 REF = "/root/reference"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
@@ -27,20 +30,8 @@ def save(name, A):
     print(name, A.shape[0], A.nnz)
 
 
-def lcc(A):
-    _, lab = connected_components(A, directed=False)
-    big = np.argmax(np.bincount(lab))     # first largest label, as the reference's loop (:163-167)
-    idx = np.where(lab == big)[0]
-    return A[idx][:, idx]
-
-
-def unweighted(A):
-    A = sp.csr_matrix(A).astype(np.float64)
-    A = A + A.T
-    A.data[:] = 1.0
-    A.setdiag(0)
-    A.eliminate_zeros()
-    return lcc(A.tocsr())
+from krylov_robustness_b200.datasets import largest_component as lcc          # noqa: E402,F401
+from krylov_robustness_b200.datasets import unweighted_adjacency as unweighted   # noqa: E402
 
 
 def main():

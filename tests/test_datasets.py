@@ -1,0 +1,38 @@
+"""datasets.py (MAT-file loading + the scripts' preprocessing) against the committed fixtures.  The reference's data
+files only exist in the build container (/root/reference); the preprocessing helpers are also tested stand-alone."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import load_graph
+
+REF = "/root/reference"
+
+
+def test_unweighted_preprocessing_on_a_toy_graph():
+    from krylov_robustness_b200.datasets import unweighted_adjacency
+    # directed, weighted, with a self loop and two components (sizes 3 and 2): keep the triangle
+    A = sp.csr_matrix((np.array([2.0, 5.0, 1.0, 7.0, 3.0]), (np.array([0, 1, 2, 3, 1]), np.array([1, 2, 0, 4, 1]))), shape=(5, 5))
+    B = unweighted_adjacency(A)
+    assert B.shape == (3, 3) and B.nnz == 6 and (B != B.T).nnz == 0
+    assert B.diagonal().sum() == 0 and set(B.data) == {1.0}
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference data files only exist in the build container")
+def test_loaders_reproduce_the_fixtures():
+    from krylov_robustness_b200 import datasets as D
+    for name, path in (("transport_Anaheim", "datasets_paper/Transport/Anaheim.mat"),
+                       ("transport_Rome", "datasets_paper/Transport/Rome.mat")):
+        A = D.load_problem(os.path.join(REF, path))
+        F = load_graph(name)
+        assert A.shape == F.shape and (A != F).nnz == 0
+    A0 = D.load_problem(os.path.join(REF, "MIOBI Codes", "dt_oregon.mat") + "::A0", unweighted=False)
+    assert (A0 != load_graph("oregon_A0")).nnz == 0
+    grids = D.load_power_grids(os.path.join(REF, "datasets_paper", "voltage_adjacencies_average_2.mat"), ["Sweden", "England"])
+    for k, A in grids.items():
+        F = load_graph("grid_" + k)
+        assert A.shape == F.shape and abs(A - F).max() <= 1e-15
+    with pytest.raises(ValueError, match="7.3"):
+        D.load_problem(os.path.join(REF, "datasets_paper", "Misc", "as_735.mat"))
