@@ -124,3 +124,23 @@ def test_greedy_break_and_make_vs_dense(graphs):
         O.greedy_krylov(sp.triu(A).tocsr(), 1, 5, c)
     with pytest.raises(ValueError, match="more than edges"):
         O.greedy_krylov(A, A.nnz, 5, c)
+
+
+def test_theta_and_expmv_against_scipys_independent_implementation(graphs):
+    """An independent anchor for the expmv family: SciPy's expm_multiply implements the same Al-Mohy - Higham 2011
+    algorithm from the paper, with its own copy of the theta table.  (1) The theta values the reference ships in
+    functions/theta_taylor.mat (oracle/theta.py, csrc/theta_table.h) equal SciPy's for every degree SciPy
+    tabulates; (2) oracle.expmv and scipy agree on e^{tA} B to 1e-12 on the reference's graphs."""
+    from scipy.sparse.linalg import expm_multiply
+    from scipy.sparse.linalg import _expm_multiply as em
+    from oracle.theta import THETA
+    import oracle as O
+    for m, th in em._theta.items():
+        # SciPy prints 2-3 significant digits; theta_1 is 2^-52 in the .mat file and 2.29e-16 in the paper's table
+        assert abs(THETA[m - 1] - th) <= 5e-2 * th, (m, THETA[m - 1], th)
+    for gname, t in (("oregon_A0", 0.25), ("transport_Rome", 1.0), ("grid_Mexico", 1.0)):
+        A = graphs(gname)
+        b = np.random.default_rng(5).standard_normal((A.shape[0], 3))
+        f = O.expmv(t, A, b)[0]
+        g = expm_multiply(t * A, b)
+        assert np.max(np.abs(f - g)) <= 1e-12 * np.max(np.abs(g))
