@@ -70,6 +70,7 @@ void kr_ctx_destroy(kr_ctx* c) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
     }
+    for (auto ev : c->free_events) cudaEventDestroy(ev);
     c->trim();
     if (c->cusolver) cusolverDnDestroy(c->cusolver);
     if (c->cublas) cublasDestroy(c->cublas);
@@ -103,8 +104,8 @@ int kr_ctx_spmm_time(kr_ctx* c, int reset, double* ms, int64_t* launches) {
             KR_CUDA(cudaEventElapsedTime(&t, ev.first, ev.second));
             c->spmm_ms += t;
             c->spmm_timed += 1;
-            cudaEventDestroy(ev.first);
-            cudaEventDestroy(ev.second);
+            c->free_events.push_back(ev.first);
+            c->free_events.push_back(ev.second);
         }
         c->spmm_events.clear();
         if (ms) *ms = c->spmm_ms;

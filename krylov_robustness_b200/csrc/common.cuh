@@ -94,6 +94,14 @@ struct kr_ctx {
     // optional SpMM timing
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spmm_events;
+    std::vector<cudaEvent_t> free_events;   // recycled timing events (no cudaEventCreate inside a timed loop)
+    void timing_events(cudaEvent_t* a, cudaEvent_t* b) {
+        cudaEvent_t* out[2] = {a, b};
+        for (auto* o : out) {
+            if (!free_events.empty()) { *o = free_events.back(); free_events.pop_back(); }
+            else if (cudaEventCreate(o) != cudaSuccess) throw std::runtime_error("cudaEventCreate failed");
+        }
+    }
     double spmm_ms = 0.0;
     int64_t spmm_timed = 0;
     // size-bucketed free lists (bytes rounded up to a power of two >= 512)

@@ -41,6 +41,7 @@ struct CsrDevView {
     const double* __restrict__ val;   // nullptr => all values == uval
     double uval;
     const int* __restrict__ row_order;
+    const int* __restrict__ row_pos;  // inverse of row_order: stored position of original row i
     const RowTile* __restrict__ tiles;
 };
 
@@ -56,7 +57,7 @@ constexpr int SPMM_LONG_ROW = 1024;   // rows at least this long are processed b
 
 struct CsrDev {
     int64_t n = 0, nnz = 0;
-    DevBuf<int> row_ptr, col, row_order;
+    DevBuf<int> row_ptr, col, row_order, row_pos;
     DevBuf<double> val;
     DevBuf<RowTile> tiles;
     int ntiles = 0;
@@ -71,6 +72,7 @@ struct CsrDev {
         v.val = pattern_only ? nullptr : val.p;
         v.uval = uval;
         v.row_order = row_order.p;
+        v.row_pos = row_pos.p;
         v.tiles = tiles.p;
         return v;
     }
@@ -214,6 +216,10 @@ inline void upload_csr(kr_ctx* ctx, const CsrHost& H, CsrDev& D) {
     D.ntiles = (int)P.tiles.size();
     D.row_order.reset(ctx, std::max<int64_t>(n, 1));
     if (n) D.row_order.upload(P.order.data(), n);
+    std::vector<int> pos((size_t)std::max<int64_t>(n, 1), 0);
+    for (int64_t s = 0; s < n; ++s) pos[(size_t)P.order[(size_t)s]] = (int)s;
+    D.row_pos.reset(ctx, std::max<int64_t>(n, 1));
+    if (n) D.row_pos.upload(pos.data(), n);
     D.tiles.reset(ctx, std::max<size_t>(P.tiles.size(), 1));
     if (!P.tiles.empty()) D.tiles.upload(P.tiles.data(), P.tiles.size());
     KR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging vectors die here

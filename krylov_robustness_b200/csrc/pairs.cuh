@@ -1,32 +1,29 @@
 // pairs.cuh - trace_fun_update for MANY candidate edges at once (the candidate loop of
 // functions/krylov_miobi.m:76-99 -> functions/trace_fun_update.m:60-125 -> functions/lanczos_krylov.m:73-101).
 //
-// Candidate h owns columns (2h, 2h+1) of three panel-major blocks P (previous basis block),
-// C (current), Y (work).  Basis blocks are never normalised in memory: the orthonormal block is
-// V = raw * T with a per-candidate 2x2 matrix T, so the thin QR of every step costs no pass over
-// the data.  One block-Lanczos step of the reference = 1 SpMM + 2 fused update passes:
-//   pass A  spmm<EpiGram2>: Y = A*C, raw Grams P'Y, C'Y               (CGS pass 1 coefficients)
-//   pass B  W = Y*Ma - P*Mp - C*Mc, raw Grams P'W, C'W                (CGS pass 2 coefficients)
-//   pass C  W = W - P*Mp - C*Mc, Gram W'W                             (R of the thin QR)
-// then one small CTA per candidate: QR factor from the Gram (Householder conventions of LAPACK for
-// exactly-zero columns, see DESIGN.md "rank-deficient blocks"), projected matrices Gm / tGm, two
-// Jacobi eigen-solves, the trace formula and the reference's lag-2 stopping rule.
+// A fixed set of SLOTS (two columns each) of three panel-major blocks P (previous basis block), C (current),
+// Y (work) is kept busy with candidates until the whole list is scored ("continuous batching"): a slot whose
+// candidate has converged is re-seeded with the next candidate of the queue, so every dense pass works on
+// columns that are still iterating and the cost is the SUM of the candidates' step counts, not (slowest
+// candidate of a chunk) x (chunk width) as in round 1.  Slots at different step numbers coexist: all
+// per-candidate state (step count, H blocks, transforms, lag-2 buffer) is indexed by slot.
+//
+// Basis blocks are never normalised in memory: the orthonormal block is V = raw * T with a per-slot 2x2
+// matrix T, so the thin QR of every step costs no pass over the data.
+//   step 1 (seed)   U = [e_i e_j]: A*U are two COLUMNS OF A, U'AU four entries of A, and CGS2 leaves exactly
+//                   W = A(:, [i j]) with rows i and j zeroed - built straight from the CSR rows (O(deg)), no
+//                   SpMM and no dense pass; its Gram is two sparse norms and a sorted-list intersection
+//   steps >= 2      pass A  spmm<EpiGram2>: Y = A*C, raw Grams P'Y, C'Y           (CGS pass 1 coefficients)
+//                   pass B  W = Y*Ma - P*Mp - C*Mc, raw Grams P'W, C'W            (CGS pass 2 coefficients)
+//                   pass C  W = W - P*Mp - C*Mc, Gram W'W                         (R of the thin QR)
+// then one small CTA per slot: QR factor from the Gram (Householder conventions of LAPACK for exactly-zero
+// columns, see DESIGN.md "rank-deficient blocks"), projected matrices Gm / tGm, two Jacobi eigen-solves, the
+// trace formula and the reference's lag-2 stopping rule.
 #pragma once
 #include "dense.cuh"
 #include "smalldense.cuh"
 
 namespace kr {
-
-// U block: column 2h = e_{i_h}, column 2h+1 = e_{j_h}    (functions/krylov_miobi.m:85-87)
-__global__ void pair_init_kernel(double* __restrict__ C, int64_t n, const int64_t* __restrict__ E,
-                                 int64_t nE, int64_t e0, int ncand) {
-    int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= ncand) return;
-    int64_t i = E[e0 + h] - 1, j = E[nE + e0 + h] - 1;
-    int c0 = 2 * h, c1 = 2 * h + 1;
-    C[(int64_t)(c0 / PW) * n * PW + i * PW + (c0 % PW)] = 1.0;
-    C[(int64_t)(c1 / PW) * n * PW + j * PW + (c1 % PW)] = 1.0;
-}
 
 // W = Y*Ma - P*Mp - C*Mc per candidate (coef[cand][12] = Ma, Mp, Mc row-major 2x2), in place in Y.
 // MODE 0: partial[rb][cand][8] = {P'W, C'W};  MODE 1: partial[rb][cand][4] = {w1'w1, w1'w2, w2'w2, 0}
@@ -56,8 +53,7 @@ pair_update_kernel(double* __restrict__ Y, const double* __restrict__ P, const d
         const int64_t o = po + r * PW + sub * 2;
         double2 y = *reinterpret_cast<const double2*>(Y + o);
         double2 c = *reinterpret_cast<const double2*>(C + o);
-        double2 p = make_double2(0.0, 0.0);
-        if (P) p = *reinterpret_cast<const double2*>(P + o);
+        const double2 p = *reinterpret_cast<const double2*>(P + o);
         double2 w;
         w.x = y.x * m[0] + y.y * m[2] - (p.x * m[4] + p.y * m[6]) - (c.x * m[8] + c.y * m[10]);
         w.y = y.x * m[1] + y.y * m[3] - (p.x * m[5] + p.y * m[7]) - (c.x * m[9] + c.y * m[11]);
@@ -91,41 +87,155 @@ __device__ __forceinline__ void mtm2(const double* A, const double* B, double* C
 }
 
 struct PairState {
-    int ncand, it, fun;
+    int nslots, it, fun;
     double tol, b_off;
-    double* Tp;       // [ncand][4]
-    double* Tc;       // [ncand][4]
-    double* hp;       // [ncand][4] accumulated CGS2 coefficients vs previous block (this step)
-    double* hc;       // [ncand][4] vs current block
-    double* coef;     // [ncand][12]
-    double* Hd;       // [ncand][it][4] diagonal blocks
-    double* Hs;       // [ncand][it][4] super-diagonal blocks (block (l-1, l))
-    double* Hr;       // [ncand][it][4] sub-diagonal blocks (block (l+1, l))
-    double* Xstop;    // [ncand][2]
-    double* Xm;       // [ncand]
-    int* iter;        // [ncand]
-    int* lucky;       // [ncand]
-    int* active;      // [ncand]
-    int* nactive;     // [1]
+    // ---- per slot
+    long long* cand;  // [nslots] index of the candidate in the caller's list, -1 = idle
+    int* ei;          // [nslots] 0-based end points
+    int* ej;
+    int* step;        // [nslots] block-Lanczos steps completed
+    int* flag;        // [nslots] PAIR_IDLE / PAIR_NEW (seeded, step 1 pending) / PAIR_RUN
+    double* Tp;       // [nslots][4]
+    double* Tc;       // [nslots][4]
+    double* hp;       // [nslots][4] accumulated CGS2 coefficients vs previous block (this step)
+    double* hc;       // [nslots][4] vs current block
+    double* coef;     // [nslots][12]
+    double* Hd;       // [nslots][it][4] diagonal blocks
+    double* Hs;       // [nslots][it][4] super-diagonal blocks (block (l-1, l))
+    double* Hr;       // [nslots][it][4] sub-diagonal blocks (block (l+1, l))
+    double* Xstop;    // [nslots][2]
+    double* G3;       // [nslots][4] Gram of the new block {g11, g12, g22, -}
+    // ---- finished slots of the last pair_step launch (the host re-seeds them)
+    int* fin_count;   // [1]
+    int* fin_slots;   // [nslots]
+    // ---- results, indexed by candidate
+    double* res_Xm;
+    long long* res_iter;
+    int* res_lucky;
 };
+constexpr int PAIR_IDLE = 0, PAIR_NEW = 1, PAIR_RUN = 2;
+
+// zero the two columns of every PAIR_NEW slot in the blocks P and C.  grid = (row blocks, panels)
+__global__ void __launch_bounds__(COL_THREADS)
+pair_zero_kernel(double* __restrict__ P, double* __restrict__ C, int64_t n, const int* __restrict__ flag) {
+    __shared__ int fl[LPT];
+    const int q = blockIdx.y, sub = threadIdx.x % LPT;
+    if (threadIdx.x < LPT) fl[threadIdx.x] = flag[q * LPT + threadIdx.x];
+    __syncthreads();
+    if (fl[sub] != PAIR_NEW) return;
+    const int64_t po = (int64_t)q * n * PW;
+    const int64_t r0 = (int64_t)blockIdx.x * COL_ROWS_PER_CTA;
+    const int64_t r1 = min(n, r0 + COL_ROWS_PER_CTA);
+    const double2 z = make_double2(0.0, 0.0);
+    for (int64_t r = r0 + (threadIdx.x / LPT); r < r1; r += COL_THREADS / LPT) {
+        const int64_t o = po + r * PW + sub * 2;
+        *reinterpret_cast<double2*>(P + o) = z;
+        *reinterpret_cast<double2*>(C + o) = z;
+    }
+}
+
+// fixed-order CTA sum of NV values per thread (256 threads); totals valid in thread 0
+template <int NV>
+__device__ __forceinline__ void seed_reduce(double (&v)[NV], double* smem) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = v[i];
+        for (int off = 16; off; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        v[i] = x;
+    }
+    if (lane == 0)
+        for (int i = 0; i < NV; ++i) smem[warp * NV + i] = v[i];
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int i = 0; i < NV; ++i) {
+            double s = 0.0;
+            for (int w = 0; w < COL_WARPS; ++w) s += smem[w * NV + i];
+            v[i] = s;
+        }
+}
+
+// Step 1 of a freshly assigned slot, straight from the CSR rows of its end points (one CTA per new slot):
+//   P(:, slot) = [e_i e_j],  C(:, slot) = W1 = A(:, [i j]) with rows i, j zeroed  (= A*U - U*(U'AU), the result of
+//   CGS2 at lanczos_krylov.m:86-88 - the second pass finds exactly zero coefficients), G3 = W1'W1, hc = U'AU.
+// The columns must have been zeroed (pair_zero_kernel).  Column indices of a stored row are ascending.
+__global__ void __launch_bounds__(COL_THREADS)
+pair_seed_kernel(CsrDevView A, PairState st, double* __restrict__ P, double* __restrict__ C, int64_t n,
+                 const int* __restrict__ new_slots) {
+    __shared__ double red[COL_WARPS * 6];
+    const int h = new_slots[blockIdx.x];
+    const int i = st.ei[h], j = st.ej[h];
+    const int si = A.row_pos[i], sj = A.row_pos[j];
+    const int i0 = A.row_ptr[si], i1 = A.row_ptr[si + 1];
+    const int j0 = A.row_ptr[sj], j1 = A.row_ptr[sj + 1];
+    const int c0 = 2 * h, c1 = 2 * h + 1;
+    double* Cp = C + (int64_t)(c0 / PW) * n * PW;
+    double* Pp = P + (int64_t)(c0 / PW) * n * PW;
+    const int o0 = c0 % PW, o1 = c1 % PW;
+    // acc: g11, g12, g22, a_ii, a_ij, a_jj
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int p = i0 + (int)threadIdx.x; p < i1; p += COL_THREADS) {
+        const int r = A.col[p];
+        const double v = A.val ? A.val[p] : A.uval;
+        if (r == i) { acc[3] += v; continue; }
+        if (r == j) { acc[4] += v; continue; }
+        Cp[(int64_t)r * PW + o0] = v;
+        acc[0] += v * v;
+        // partner entry A(r, j): binary search in the stored row of j
+        int lo = j0, hi = j1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (A.col[mid] < r) lo = mid + 1; else hi = mid;
+        }
+        if (lo < j1 && A.col[lo] == r) acc[1] += v * (A.val ? A.val[lo] : A.uval);
+    }
+    for (int p = j0 + (int)threadIdx.x; p < j1; p += COL_THREADS) {
+        const int r = A.col[p];
+        const double v = A.val ? A.val[p] : A.uval;
+        if (r == j) { acc[5] += v; continue; }
+        if (r == i) continue;
+        Cp[(int64_t)r * PW + o1] = v;
+        acc[2] += v * v;
+    }
+    seed_reduce<6>(acc, red);
+    if (threadIdx.x == 0) {
+        Pp[(int64_t)i * PW + o0] = 1.0;
+        Pp[(int64_t)j * PW + o1] = 1.0;
+        st.G3[h * 4 + 0] = acc[0];
+        st.G3[h * 4 + 1] = acc[1];
+        st.G3[h * 4 + 2] = acc[2];
+        st.G3[h * 4 + 3] = 0.0;
+        st.hc[h * 4 + 0] = acc[3]; st.hc[h * 4 + 1] = acc[4];
+        st.hc[h * 4 + 2] = acc[4]; st.hc[h * 4 + 3] = acc[5];
+        for (int k = 0; k < 4; ++k) {
+            st.hp[h * 4 + k] = 0.0;
+            st.Tp[h * 4 + k] = (k == 0 || k == 3) ? 1.0 : 0.0;
+            st.Tc[h * 4 + k] = (k == 0 || k == 3) ? 1.0 : 0.0;
+        }
+        st.Xstop[h * 2] = st.Xstop[h * 2 + 1] = 0.0;
+        st.step[h] = 0;
+    }
+}
 
 // after pass A: h = T' G T (first CGS pass), coefficients of pass B
-__global__ void pair_coef1_kernel(PairState st, const double* __restrict__ G, int first) {
+__global__ void pair_coef1_kernel(PairState st, const double* __restrict__ G) {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= st.ncand) return;
+    if (h >= st.nslots) return;
+    double* cf = st.coef + (int64_t)h * 12;
+    if (st.flag[h] != PAIR_RUN) {
+        for (int i = 0; i < 12; ++i) cf[i] = 0.0;       // idle slot: its columns stay finite (zero)
+        return;
+    }
     const double* g = G + (int64_t)h * 8;
     const double* Tc = st.Tc + h * 4;
     const double* Tp = st.Tp + h * 4;
-    double tmp[4], hp[4] = {0, 0, 0, 0}, hc[4], Mp[4] = {0, 0, 0, 0}, Mc[4];
+    double tmp[4], hp[4], hc[4], Mp[4], Mc[4];
     mm2(g + 4, Tc, tmp);       // (C'Y) Tc
     mtm2(Tc, tmp, hc);         // Tc' (C'Y) Tc
     mm2(Tc, hc, Mc);
-    if (!first) {
-        mm2(g, Tc, tmp);
-        mtm2(Tp, tmp, hp);
-        mm2(Tp, hp, Mp);
-    }
-    double* cf = st.coef + (int64_t)h * 12;
+    mm2(g, Tc, tmp);
+    mtm2(Tp, tmp, hp);
+    mm2(Tp, hp, Mp);
     for (int i = 0; i < 4; ++i) {
         cf[i] = Tc[i];
         cf[4 + i] = Mp[i];
@@ -136,19 +246,18 @@ __global__ void pair_coef1_kernel(PairState st, const double* __restrict__ G, in
 }
 
 // after pass B: h1 = T' G (W already carries T), h += h1, coefficients of pass C
-__global__ void pair_coef2_kernel(PairState st, const double* __restrict__ G, int first) {
+__global__ void pair_coef2_kernel(PairState st, const double* __restrict__ G) {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= st.ncand) return;
+    if (h >= st.nslots) return;
+    if (st.flag[h] != PAIR_RUN) return;               // coefficients of an idle slot stay zero
     const double* g = G + (int64_t)h * 8;
     const double* Tc = st.Tc + h * 4;
     const double* Tp = st.Tp + h * 4;
-    double hp[4] = {0, 0, 0, 0}, hc[4], Mp[4] = {0, 0, 0, 0}, Mc[4];
+    double hp[4], hc[4], Mp[4], Mc[4];
     mtm2(Tc, g + 4, hc);
     mm2(Tc, hc, Mc);
-    if (!first) {
-        mtm2(Tp, g, hp);
-        mm2(Tp, hp, Mp);
-    }
+    mtm2(Tp, g, hp);
+    mm2(Tp, hp, Mp);
     double* cf = st.coef + (int64_t)h * 12;
     cf[0] = 1.0; cf[1] = 0.0; cf[2] = 0.0; cf[3] = 1.0;
     for (int i = 0; i < 4; ++i) {
@@ -159,17 +268,21 @@ __global__ void pair_coef2_kernel(PairState st, const double* __restrict__ G, in
     }
 }
 
-// One CTA per candidate, after pass C of step j (1-based).  G3[cand][4] = {g11, g12, g22, -}.
-// W is the panel-major block holding the orthogonalised (un-normalised) new block.
+// One CTA per slot in state `mode` (PAIR_NEW: finish step 1 after the seed; PAIR_RUN: finish step step+1 after
+// pass C).  G3[slot][4] = {g11, g12, g22, -}; W is the panel-major block holding the orthogonalised
+// (un-normalised) new block.  gscratch (may be null): per-slot global work space used instead of shared memory
+// when the projected matrices outgrow it (2j > ~110).
 __global__ void __launch_bounds__(JAC_THREADS)
-pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict__ W, int64_t n, int j) {
+pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict__ W, int64_t n, int mode,
+                 double* __restrict__ gscratch, int64_t gscratch_stride) {
     extern __shared__ double dyn[];
     __shared__ JacobiShared sh;
     __shared__ double Tn[4];
     __shared__ int s_lucky;
     const int h = blockIdx.x;
-    if (!st.active[h]) return;
+    if (st.flag[h] != mode) return;
     const int it = st.it;
+    const int j = st.step[h] + 1;
     double* Hd = st.Hd + ((int64_t)h * it) * 4;
     double* Hs = st.Hs + ((int64_t)h * it) * 4;
     double* Hr = st.Hr + ((int64_t)h * it) * 4;
@@ -242,8 +355,8 @@ pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict
     __syncthreads();
     // ---- projected matrices: Gm = H(1:2j, 1:2j) symmetrised, tGm = Gm + Cm    (trace_fun_update.m:72-81)
     const int nn = 2 * j, lda = nn | 1;
-    double* G = dyn;
-    double* tG = dyn + nn * lda;
+    double* G = gscratch ? gscratch + (int64_t)h * gscratch_stride : dyn;
+    double* tG = G + nn * lda;
     double* d1 = tG + nn * lda;
     double* d2 = d1 + nn;
     for (int e = threadIdx.x; e < nn * nn; e += JAC_THREADS) {
@@ -280,12 +393,16 @@ pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict
         }
         if (!done && s_lucky) done = true;
         if (j == it) done = true;
-        st.Xm[h] = Xm;
-        st.iter[h] = j;
-        st.lucky[h] = s_lucky;
+        const long long cand = st.cand[h];
+        st.res_Xm[cand] = Xm;
+        st.res_iter[cand] = j;
+        st.res_lucky[cand] = s_lucky;
+        st.step[h] = j;
         if (done) {
-            st.active[h] = 0;
-            atomicSub(st.nactive, 1);
+            st.flag[h] = PAIR_IDLE;
+            st.fin_slots[atomicAdd(st.fin_count, 1)] = h;
+        } else {
+            st.flag[h] = PAIR_RUN;
         }
         // rotate transforms: previous <- current, current <- new
         for (int i = 0; i < 4; ++i) {
@@ -295,122 +412,192 @@ pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict
     }
 }
 
-// panel_active[q] = any candidate of panel q still iterating (lets the SpMM and the update passes skip
-// whole panels: candidates converge after 3..11 steps)
-__global__ void pair_panel_active_kernel(const int* __restrict__ active, int ncp, int* __restrict__ panel_active) {
+// panel_active[q] = any slot of panel q still iterating (lets the SpMM and the update passes skip whole
+// panels; only matters once the queue has run dry)
+__global__ void pair_panel_active_kernel(const int* __restrict__ flag, int nslots, int* __restrict__ panel_active) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q * LPT >= ncp) return;
+    if (q * LPT >= nslots) return;
     int any = 0;
-    for (int i = 0; i < LPT; ++i) any |= active[q * LPT + i];
+    for (int i = 0; i < LPT; ++i) any |= (flag[q * LPT + i] == PAIR_RUN);
     panel_active[q] = any;
 }
 
-struct PairResult {
-    std::vector<double> Xm;
-    std::vector<int> iter, lucky;
-};
-
-// Scores candidates E[e0 .. e0+ncand) (E is nE x 2 column-major on the DEVICE, 1-based, i != j).
-inline void pairs_run_chunk(kr_ctx* ctx, const kr_matrix* M, const int64_t* E_dev, int64_t nE, int64_t e0,
-                            int ncand, double b_off, double tol, int it, int fun, double* Xm_out,
-                            int64_t* iter_out, int* lucky_out) {
+// Scores the candidates (i_q, j_q), q < np (1-based end points, i != j, n > 130) and writes Xm / iter / lucky
+// in candidate order.  max_slots bounds the three n x (2*slots) work blocks.
+inline void pairs_run(kr_ctx* ctx, const kr_matrix* M, const int64_t* Ei, const int64_t* Ej, int64_t np, int64_t max_slots,
+                      double b_off, double tol, int it, int fun, double* Xm_out, int64_t* iter_out, int* lucky_out) {
+    if (np <= 0) return;
     const CsrDev& A = M->dev;
     const int64_t n = A.n;
-    const int cols = 2 * ncand;
-    PanelBuf B0(ctx, n, cols), B1(ctx, n, cols), B2(ctx, n, cols);
+    const int nslots_req = (int)std::min<int64_t>(np, std::max<int64_t>(LPT, max_slots));
+    PanelBuf B0(ctx, n, 2 * nslots_req), B1(ctx, n, 2 * nslots_req), B2(ctx, n, 2 * nslots_req);
     const int panels = B0.panels;
-    const int ncp = panels * LPT;                     // candidates padded to whole panels
+    const int ns = panels * LPT;                      // slots padded to whole panels
     B0.buf.zero();
     B1.buf.zero();
     B2.buf.zero();
     const int rb = col_row_blocks(n);
     const int nparts = std::max(rb, A.ntiles);
-    DevBuf<double> partial(ctx, (size_t)nparts * ncp * 8), Gsum(ctx, (size_t)ncp * 8);
-    DevBuf<double> dstate(ctx, (size_t)ncp * (4 + 4 + 4 + 4 + 12 + 2 + 1) + (size_t)ncp * it * 12);
-    DevBuf<int> istate(ctx, (size_t)ncp * 3 + 1), pact(ctx, panels);
+    DevBuf<double> partial(ctx, (size_t)nparts * ns * 8), Gsum(ctx, (size_t)ns * 8);
+    DevBuf<double> dstate(ctx, (size_t)ns * (4 + 4 + 4 + 4 + 12 + 2 + 4) + (size_t)ns * it * 12);
+    DevBuf<int> istate(ctx, (size_t)ns * 6 + 1), pact(ctx, panels);
+    DevBuf<long long> cand(ctx, ns), res_iter(ctx, np);
+    DevBuf<double> res_x(ctx, np);
+    DevBuf<int> res_lucky(ctx, np);
     dstate.zero();
     istate.zero();
     PairState st;
-    st.ncand = ncand; st.it = it; st.fun = fun; st.tol = tol; st.b_off = b_off;
+    st.nslots = ns; st.it = it; st.fun = fun; st.tol = tol; st.b_off = b_off;
     double* d = dstate.p;
-    st.Tp = d; d += ncp * 4;
-    st.Tc = d; d += ncp * 4;
-    st.hp = d; d += ncp * 4;
-    st.hc = d; d += ncp * 4;
-    st.coef = d; d += ncp * 12;
-    st.Xstop = d; d += ncp * 2;
-    st.Xm = d; d += ncp;
-    st.Hd = d; d += (size_t)ncp * it * 4;
-    st.Hs = d; d += (size_t)ncp * it * 4;
+    st.Tp = d; d += ns * 4;
+    st.Tc = d; d += ns * 4;
+    st.hp = d; d += ns * 4;
+    st.hc = d; d += ns * 4;
+    st.coef = d; d += ns * 12;
+    st.Xstop = d; d += ns * 2;
+    st.G3 = d; d += ns * 4;
+    st.Hd = d; d += (size_t)ns * it * 4;
+    st.Hs = d; d += (size_t)ns * it * 4;
     st.Hr = d;
-    st.iter = istate.p;
-    st.lucky = istate.p + ncp;
-    st.active = istate.p + 2 * ncp;
-    st.nactive = istate.p + 3 * ncp;
-    // identity transforms, everything active
-    std::vector<double> Tinit((size_t)ncp * 4, 0.0);
-    for (int h = 0; h < ncp; ++h) { Tinit[h * 4] = 1.0; Tinit[h * 4 + 3] = 1.0; }
-    KR_CUDA(cudaMemcpyAsync(st.Tc, Tinit.data(), Tinit.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    KR_CUDA(cudaMemcpyAsync(st.Tp, Tinit.data(), Tinit.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<int> act(ncp + 1, 0);
-    for (int h = 0; h < ncand; ++h) act[h] = 1;
-    KR_CUDA(cudaMemcpyAsync(st.active, act.data(), (size_t)ncp * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    int nact = ncand;
-    KR_CUDA(cudaMemcpyAsync(st.nactive, &nact, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    KR_LAUNCH(ctx, pair_panel_active_kernel, (int)ceil_div(panels, 128), 128, 0, st.active, ncp, pact.p);
-    KR_CUDA(cudaStreamSynchronize(ctx->stream));
+    st.ei = istate.p;
+    st.ej = istate.p + ns;
+    st.step = istate.p + 2 * ns;
+    st.flag = istate.p + 3 * ns;
+    st.fin_slots = istate.p + 4 * ns;
+    int* new_slots_dev = istate.p + 5 * ns;
+    st.fin_count = istate.p + 6 * ns;
+    st.cand = cand.p;
+    st.res_Xm = res_x.p;
+    st.res_iter = res_iter.p;
+    st.res_lucky = res_lucky.p;
 
-    double* C = B0.p();
-    double* P = nullptr;
-    double* Y = B1.p();
-    double* spare = B2.p();
-    KR_LAUNCH(ctx, pair_init_kernel, (int)ceil_div(ncand, 128), 128, 0, C, n, E_dev, nE, e0, ncand);
-    const int cb = (int)ceil_div(ncp, 128);
-    const int sb8 = (int)ceil_div((int64_t)ncp * 8, 128), sb4 = (int)ceil_div((int64_t)ncp * 4, 128);
-    dim3 ugrid((unsigned)rb, (unsigned)panels);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (first_use_on_device(attr_set, ctx->device))
         KR_CUDA(cudaFuncSetAttribute(pair_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_LIMIT));
-        attr_set = true;
-    }
-    for (int j = 1; j <= it; ++j) {
-        const int first = (j == 1);
+
+    // host mirror of the slot table
+    std::vector<long long> h_cand(ns, -1);
+    std::vector<int> h_ei(ns, 0), h_ej(ns, 0), h_flag(ns, PAIR_IDLE), h_step(ns, 0), h_new, h_fin(ns);
+    int64_t next = 0;
+    int running = 0;
+    double* P = B0.p();
+    double* C = B1.p();
+    double* Y = B2.p();
+    const int cb = (int)ceil_div(ns, 128);
+    dim3 ugrid((unsigned)rb, (unsigned)panels);
+    DevBuf<double> gscratch;                           // only when the projections outgrow shared memory
+    auto step_smem = [&](int jmax, int64_t* stride) -> size_t {
+        const int nn = 2 * jmax;
+        const size_t need = (size_t)(2 * nn * (nn | 1) + 2 * nn) * sizeof(double);
+        if (need <= JAC_SMEM_LIMIT) { *stride = 0; return need; }
+        const int nn_it = 2 * it;
+        *stride = (int64_t)2 * nn_it * (nn_it | 1) + 2 * nn_it;
+        if (!gscratch.p) gscratch.reset(ctx, (size_t)ns * (size_t)*stride);
+        return 0;
+    };
+    auto launch_step = [&](double* W, int mode, int jmax) {
+        int64_t stride = 0;
+        const size_t smem = step_smem(jmax, &stride);
+        KR_LAUNCH(ctx, pair_step_kernel, ns, JAC_THREADS, smem, st, st.G3, W, n, mode, stride ? gscratch.p : (double*)nullptr, stride);
+    };
+    std::vector<int> free_slots(ns);
+    for (int h = 0; h < ns; ++h) free_slots[h] = ns - 1 - h;     // pop from the back: slot 0 first
+    for (;;) {
+        // ---- (re-)seed idle slots from the queue
+        h_new.clear();
+        while (next < np && !free_slots.empty()) {
+            const int h = free_slots.back();
+            free_slots.pop_back();
+            h_cand[h] = next;
+            h_ei[h] = (int)(Ei[next] - 1);
+            h_ej[h] = (int)(Ej[next] - 1);
+            h_flag[h] = PAIR_NEW;
+            h_step[h] = 0;
+            h_new.push_back(h);
+            ++next;
+        }
+        if (!h_new.empty()) {
+            // the slot tables are small: ship them whole (flags of running slots are unchanged on both sides)
+            KR_CUDA(cudaMemcpyAsync(st.cand, h_cand.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+            KR_CUDA(cudaMemcpyAsync(st.ei, h_ei.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            KR_CUDA(cudaMemcpyAsync(st.ej, h_ej.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            KR_CUDA(cudaMemcpyAsync(st.flag, h_flag.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            KR_CUDA(cudaMemcpyAsync(new_slots_dev, h_new.data(), h_new.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->counters[3] += (int64_t)ns * 20;
+            KR_LAUNCH(ctx, pair_zero_kernel, ugrid, COL_THREADS, 0, P, C, n, st.flag);
+            KR_LAUNCH(ctx, pair_seed_kernel, (int)h_new.size(), COL_THREADS, 0, A.view(), st, P, C, n, new_slots_dev);
+            launch_step(C, PAIR_NEW, 1);
+            for (int h : h_new) { h_flag[h] = PAIR_RUN; h_step[h] = 1; }
+            running += (int)h_new.size();
+            // a seeded slot can finish at step 1 (it == 1 or a lucky breakdown): collect before the dense step
+            int nfin = 0;
+            KR_CUDA(cudaMemcpyAsync(&nfin, st.fin_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            KR_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (nfin > 0) {
+                KR_CUDA(cudaMemcpyAsync(h_fin.data(), st.fin_slots, nfin * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                KR_CUDA(cudaMemsetAsync(st.fin_count, 0, sizeof(int), ctx->stream));
+                KR_CUDA(cudaStreamSynchronize(ctx->stream));
+                for (int k = 0; k < nfin; ++k) {
+                    const int h = h_fin[k];
+                    h_flag[h] = PAIR_IDLE; h_cand[h] = -1;
+                    free_slots.push_back(h);
+                }
+                running -= nfin;
+                if (next < np) continue;               // re-seed those right away
+            }
+        }
+        if (running == 0) break;
+        // ---- one dense block-Lanczos step for every running slot
+        int jmax = 0;
+        for (int h = 0; h < ns; ++h)
+            if (h_flag[h] == PAIR_RUN) jmax = std::max(jmax, h_step[h] + 1);
+        KR_LAUNCH(ctx, pair_panel_active_kernel, (int)ceil_div(panels, 128), 128, 0, st.flag, ns, pact.p);
         EpiGram2 epi;
-        epi.Y = Y; epi.P = P; epi.C = C; epi.partial = partial.p; epi.ncand = ncp;
-        launch_spmm(ctx, A, C, panels, epi, nullptr, cols, pact.p);
-        sum_partials(ctx, partial.p, A.ntiles, ncp * 8, Gsum.p);
-        KR_LAUNCH(ctx, pair_coef1_kernel, cb, 128, 0, st, Gsum.p, first);
-        KR_LAUNCH(ctx, pair_update_kernel<0>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ncp, partial.p, pact.p);
-        sum_partials(ctx, partial.p, rb, ncp * 8, Gsum.p);
-        KR_LAUNCH(ctx, pair_coef2_kernel, cb, 128, 0, st, Gsum.p, first);
-        KR_LAUNCH(ctx, pair_update_kernel<1>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ncp, partial.p, pact.p);
-        sum_partials(ctx, partial.p, rb, ncp * 4, Gsum.p);
-        const int nn = 2 * j;
-        const size_t smem = (size_t)(2 * nn * (nn | 1) + 2 * nn) * sizeof(double);
-        if (smem > JAC_SMEM_LIMIT)
-            fail(KR_ERR_UNSUPPORTED, "trace_fun_update_edges: projected size %d exceeds the shared-memory solver", nn);
-        KR_LAUNCH(ctx, pair_step_kernel, ncand, JAC_THREADS, smem, st, Gsum.p, Y, n, j);
-        KR_LAUNCH(ctx, pair_panel_active_kernel, (int)ceil_div(panels, 128), 128, 0, st.active, ncp, pact.p);
+        epi.Y = Y; epi.P = P; epi.C = C; epi.partial = partial.p; epi.ncand = ns;
+        launch_spmm(ctx, A, C, panels, epi, nullptr, 2 * running, pact.p);
+        sum_partials(ctx, partial.p, A.ntiles, ns * 8, Gsum.p);
+        KR_LAUNCH(ctx, pair_coef1_kernel, cb, 128, 0, st, Gsum.p);
+        KR_LAUNCH(ctx, pair_update_kernel<0>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ns, partial.p, pact.p);
+        sum_partials(ctx, partial.p, rb, ns * 8, Gsum.p);
+        KR_LAUNCH(ctx, pair_coef2_kernel, cb, 128, 0, st, Gsum.p);
+        KR_LAUNCH(ctx, pair_update_kernel<1>, ugrid, COL_THREADS, 0, Y, P, C, n, st.coef, ns, partial.p, pact.p);
+        sum_partials(ctx, partial.p, rb, ns * 4, st.G3);
+        launch_step(Y, PAIR_RUN, jmax);
         // rotate blocks: previous <- current, current <- W
-        double* oldP = P ? P : spare;
+        double* oldP = P;
         P = C;
         C = Y;
         Y = oldP;
-        KR_CUDA(cudaMemcpyAsync(&nact, st.nactive, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        for (int h = 0; h < ns; ++h)
+            if (h_flag[h] == PAIR_RUN) h_step[h] += 1;
+        int nfin = 0;
+        KR_CUDA(cudaMemcpyAsync(&nfin, st.fin_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         KR_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (nact <= 0) break;
+        if (nfin > 0) {
+            KR_CUDA(cudaMemcpyAsync(h_fin.data(), st.fin_slots, nfin * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            KR_CUDA(cudaMemsetAsync(st.fin_count, 0, sizeof(int), ctx->stream));
+            KR_CUDA(cudaStreamSynchronize(ctx->stream));
+            std::sort(h_fin.begin(), h_fin.begin() + nfin);      // the device appends in completion order
+            for (int k = nfin - 1; k >= 0; --k) {
+                const int h = h_fin[k];
+                h_flag[h] = PAIR_IDLE; h_cand[h] = -1;
+                free_slots.push_back(h);
+            }
+            running -= nfin;
+        }
     }
-    std::vector<double> xm(ncp);
-    std::vector<int> itv(ncp), lk(ncp);
-    KR_CUDA(cudaMemcpyAsync(xm.data(), st.Xm, ncp * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    KR_CUDA(cudaMemcpyAsync(itv.data(), st.iter, ncp * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    KR_CUDA(cudaMemcpyAsync(lk.data(), st.lucky, ncp * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<double> xm(np);
+    std::vector<long long> itv(np);
+    std::vector<int> lk(np);
+    KR_CUDA(cudaMemcpyAsync(xm.data(), st.res_Xm, np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    KR_CUDA(cudaMemcpyAsync(itv.data(), st.res_iter, np * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    KR_CUDA(cudaMemcpyAsync(lk.data(), st.res_lucky, np * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     KR_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->counters[4] += ncp * 16;
-    for (int h = 0; h < ncand; ++h) {
-        Xm_out[h] = xm[h];
-        iter_out[h] = itv[h];
-        lucky_out[h] = lk[h];
+    ctx->counters[4] += np * 20;
+    for (int64_t q = 0; q < np; ++q) {
+        Xm_out[q] = xm[q];
+        iter_out[q] = itv[q];
+        lucky_out[q] = lk[q];
     }
 }
 

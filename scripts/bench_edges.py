@@ -40,6 +40,7 @@ def main():
     step_bytes = 96.0 * n * 2 * E.shape[0]            # SpMM dense side 32 + two update passes 64 B per row per column
     print(json.dumps({"candidates": int(E.shape[0]), "seconds": dt, "edges_per_sec": E.shape[0] / dt,
                       "block_lanczos_steps_max": steps, "steps_mean": float(it.mean()),
+                      "steps_histogram": {int(k): int(v) for k, v in zip(*np.unique(it, return_counts=True))},
                       "spmm_ms": ms, "spmm_launches": nl, "spmm_share": ms * 1e-3 / dt,
                       "launches": c1["launches"] - c0["launches"],
                       "dense_bytes_per_step_GB": step_bytes / 1e9,

@@ -111,6 +111,36 @@ def test_trace_fun_update_edges_vs_oracle(kr, O, graphs, gname, fun, sign):
     assert abs(x2 - x[0]) <= 1e-8 * abs(x[0])
 
 
+def test_trace_fun_update_edges_slot_reseeding(kr, O, graphs, monkeypatch):
+    """The candidate pipeline keeps a fixed number of slots busy and re-seeds a slot as soon as its candidate has
+    converged (slots at different step numbers coexist).  With 8 / 24 slots for 96 candidates every slot is
+    re-used many times: values, iteration counts and lucky flags must not depend on the slot count, and match
+    the oracle."""
+    A = graphs("oregon_A8")
+    n = A.shape[0]
+    nrm, _ = O.normest(A, 1e-2)
+    tol = 1e-6 * np.exp(nrm)
+    c = O.compute_centrality(A, "eig")
+    E = np.concatenate([O.find_top_edges(A, c, 48, "min"), O.find_top_missing_edges(A, c, 48, "min")])
+    ref = None
+    for slots in ("", "8", "24"):
+        if slots:
+            monkeypatch.setenv("KR_PAIR_SLOTS", slots)
+        res = [kr.trace_fun_update_edges(A, E[:48], -1.0, tol, 100, "exp"),
+               kr.trace_fun_update_edges(A, E[48:], 1.0, tol, 100, "exp")]
+        if ref is None:
+            ref = res
+        for (x, it, lk), (x0, it0, lk0) in zip(res, ref):
+            assert np.array_equal(it, it0) and np.array_equal(lk, lk0)
+            assert np.array_equal(x, x0), np.abs(x - x0).max()      # slot placement does not change the arithmetic
+    for h in range(0, 96, 5):
+        sign = -1.0 if h < 48 else 1.0
+        U, B = edge_UB(n, int(E[h, 0]), int(E[h, 1]), sign)
+        ox, oit, _ = O.trace_fun_update(A, U, B, tol, 100)
+        x, it, _ = ref[0 if h < 48 else 1]
+        assert it[h % 48] == oit and abs(x[h % 48] - ox) <= RTOL * abs(ox)
+
+
 def test_trace_fun_update_edges_with_leaf_endpoints(kr, O, graphs):
     """Edges with a degree-1 endpoint: the first Lanczos block of a (leaf, hub) edge has an exactly zero
     column and the reference continues with LAPACK's Householder completion (a coordinate vector,
