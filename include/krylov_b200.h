@@ -108,6 +108,11 @@ int  kr_trace_fun_update(kr_ctx* ctx, const kr_matrix* A, int64_t rk, const doub
 int  kr_trace_fun_update_edges(kr_ctx* ctx, const kr_matrix* A, int64_t nE, const int64_t* E,
                                double b_offdiag, double tol, int64_t it, int fun,
                                double* Xm, int64_t* iter, int* lucky);
+/* Same with the rank-one value given separately: the reference does NOT divide the self-loop update by
+ * `rescale` (functions/krylov_miobi.m:88-94: B = -1 / B = 1), only the rank-two one (:78-80). */
+int  kr_trace_fun_update_edges_ex(kr_ctx* ctx, const kr_matrix* A, int64_t nE, const int64_t* E,
+                                  double b_offdiag, double b_self, double tol, int64_t it, int fun,
+                                  double* Xm, int64_t* iter, int* lucky);
 /* [Xm,iter,lucky,Um] = fun_update(A,U,B,fun,tol,it,debug)       functions/fun_update.m:1-137
  * want_basis stands in for nargout == 4 (:69,:77).  Xm is returned column-major with leading
  * dimension xm_dim; Um (n x xm_dim, or the Lanczos window) only if want_basis.  Call with

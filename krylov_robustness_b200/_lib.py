@@ -47,6 +47,8 @@ PROTOTYPES = {
                             c_dp, c_ip, c_intp],
     "kr_trace_fun_update_edges": [VP, VP, c_i64, VP, C.c_double, C.c_double, c_i64, C.c_int,
                                   VP, VP, VP],
+    "kr_trace_fun_update_edges_ex": [VP, VP, c_i64, VP, C.c_double, C.c_double, C.c_double, c_i64, C.c_int,
+                                     VP, VP, VP],
     "kr_fun_update": [VP, VP, c_i64, VP, c_i64, VP, c_i64, C.c_int, C.c_double, c_i64, C.c_int,
                       c_ip, c_ip, c_intp, c_intp],
     "kr_fun_update_fetch": [VP, VP, c_i64, VP, c_i64],

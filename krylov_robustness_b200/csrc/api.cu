@@ -10,6 +10,9 @@
 #include "smalldense.cuh"
 #include "pairs.cuh"
 #include "expmv.cuh"
+#include "tsdense.cuh"
+#include "smallgemm.cuh"
+#include "vecops.cuh"
 #include "blockkrylov.cuh"
 #include "entries.cuh"
 #include "frechet.cuh"
@@ -52,11 +55,6 @@ int kr_ctx_create(int device, kr_ctx** out) {
         c->num_sms = prop.multiProcessorCount;
         c->l2_bytes = (size_t)prop.l2CacheSize;
         KR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        KR_CUBLAS(cublasCreate(&c->cublas));
-        KR_CUBLAS(cublasSetStream(c->cublas, c->stream));
-        KR_CUBLAS(cublasSetPointerMode(c->cublas, CUBLAS_POINTER_MODE_HOST));
-        KR_CUSOLVER(cusolverDnCreate(&c->cusolver));
-        KR_CUSOLVER(cusolverDnSetStream(c->cusolver, c->stream));
         *out = c;
     });
 }
@@ -72,8 +70,6 @@ void kr_ctx_destroy(kr_ctx* c) {
     }
     for (auto ev : c->free_events) cudaEventDestroy(ev);
     c->trim();
-    if (c->cusolver) cusolverDnDestroy(c->cusolver);
-    if (c->cublas) cublasDestroy(c->cublas);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -239,33 +235,8 @@ void kr_dense_destroy(kr_dense* d) {
     delete d;
 }
 
-static void upload_cm(kr_ctx* ctx, const double* host, int64_t ld, PanelBuf& dst) {
-    const int64_t n = dst.n;
-    const int k = dst.cols;
-    if (ld < n) fail(KR_ERR_ARG, "leading dimension smaller than the number of rows");
-    DevBuf<double> stage(ctx, (size_t)std::max<int64_t>(n * k, 1));
-    if (n > 0 && k > 0) {
-        KR_CUDA(cudaMemcpy2DAsync(stage.p, n * sizeof(double), host, ld * sizeof(double), n * sizeof(double), k,
-                                  cudaMemcpyHostToDevice, ctx->stream));
-        ctx->counters[3] += n * k * (int64_t)sizeof(double);
-    }
-    cm_to_panel(ctx, stage.p, n, dst);
-    KR_CUDA(cudaStreamSynchronize(ctx->stream));   // the caller's host buffer may go away
-}
-
-static void download_cm(kr_ctx* ctx, const PanelBuf& src, double* host, int64_t ld) {
-    const int64_t n = src.n;
-    const int k = src.cols;
-    if (ld < n) fail(KR_ERR_ARG, "leading dimension smaller than the number of rows");
-    DevBuf<double> stage(ctx, (size_t)std::max<int64_t>(n * k, 1));
-    panel_to_cm(ctx, src, stage.p, n);
-    if (n > 0 && k > 0) {
-        KR_CUDA(cudaMemcpy2DAsync(host, ld * sizeof(double), stage.p, n * sizeof(double), n * sizeof(double), k,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->counters[4] += n * k * (int64_t)sizeof(double);
-    }
-    KR_CUDA(cudaStreamSynchronize(ctx->stream));
-}
+static void upload_cm(kr_ctx* ctx, const double* host, int64_t ld, PanelBuf& dst) { upload_cm_block(ctx, host, ld, dst); }
+static void download_cm(kr_ctx* ctx, const PanelBuf& src, double* host, int64_t ld) { download_cm_block(ctx, src, host, ld); }
 
 int kr_dense_upload(kr_dense* d, const double* host, int64_t ld) {
     return guarded([&] {

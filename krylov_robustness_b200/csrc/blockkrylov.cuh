@@ -1,35 +1,24 @@
 // blockkrylov.cuh - general-width block Lanczos / Arnoldi (functions/lanczos_krylov.m,
 // functions/arnoldi_krylov.m) and the evaluators built on them with one wide block:
-// trace_fun_update (rk > 2), fun_update, fun_and_grad_krylov_*, mc_trace, normest.
+// trace_fun_update (rk > 2), fun_update, fun_and_grad_krylov_*, normest.
 //
-// Blocks live on the device column-major (n x bs, MATLAB layout) so that the tall-skinny Gram /
-// update products are plain library GEMMs (cuBLAS dgemm -> FP64 DMMA on B200) and the thin QR is
-// cuSOLVER's Householder geqrf/orgqr - the same factorisation (and sign / zero-column conventions)
-// as the reference's qr(w,0).  The SpMM runs on the panel-major copy (two cheap transposes per
-// step).  The small projected matrices (H, K, Cm, Gm) live on the host; their eigen-solves run on
-// the device (Jacobi kernel for n <= 110, cuSOLVER syevd above).
+// Everything runs in hand-written kernels on PANEL-MAJOR blocks (the SpMM's own layout, no transposes):
+//   one add_inf_pole step = SpMM -> Gram V'W (DMMA) -> W -= V h -> Gram -> W -= V h1 -> Householder QR
+//   (dgeqr2/dorg2r semantics, tsdense.cuh) [-> Arnoldi's third pass], with h, h1, R written straight into the
+//   device-resident block storage of H.  The projected matrices Gm / tGm are assembled on the device, f(Gm) is a
+//   GEMM-based scaling-and-squaring Taylor evaluation (smallgemm.cuh), the stopping quantities are reduced on
+//   the device; per Krylov step the host reads back a handful of scalars (one synchronisation).
+// No cuBLAS / cuSOLVER anywhere (round 1 used dgemm / geqrf / orgqr / syevd here).
 #pragma once
 #include <chrono>
 #include <memory>
 
 #include "dense.cuh"
 #include "smalldense.cuh"
+#include "smallgemm.cuh"
+#include "vecops.cuh"
 
 namespace kr {
-
-struct CmMat {                       // owning column-major device matrix, ld == rows
-    DevBuf<double> buf;
-    int64_t rows = 0, cols = 0;
-    CmMat() = default;
-    CmMat(kr_ctx* ctx, int64_t r, int64_t c) { reset(ctx, r, c); }
-    void reset(kr_ctx* ctx, int64_t r, int64_t c) {
-        rows = r;
-        cols = c;
-        buf.reset(ctx, (size_t)std::max<int64_t>(r * c, 1));
-    }
-    double* p() const { return buf.p; }
-    double* col(int64_t c) const { return buf.p + c * rows; }
-};
 
 struct HostMat {                     // small column-major host matrix
     int64_t rows = 0, cols = 0;
@@ -38,277 +27,220 @@ struct HostMat {                     // small column-major host matrix
     HostMat(int64_t r, int64_t c) : rows(r), cols(c), a((size_t)(r * c), 0.0) {}
     double& operator()(int64_t i, int64_t j) { return a[(size_t)(i + j * rows)]; }
     double operator()(int64_t i, int64_t j) const { return a[(size_t)(i + j * rows)]; }
-    void grow(int64_t r, int64_t c) {     // zero-padded enlarge (H(end+bs, end+bs) = 0)
-        HostMat n(r, c);
-        for (int64_t j = 0; j < cols; ++j)
-            for (int64_t i = 0; i < rows; ++i) n(i, j) = (*this)(i, j);
-        *this = std::move(n);
-    }
 };
 
-inline void upload_host_cm(kr_ctx* ctx, const double* host, int64_t ld, CmMat& dst) {
-    if (dst.rows == 0 || dst.cols == 0) return;
-    KR_CUDA(cudaMemcpy2DAsync(dst.p(), dst.rows * sizeof(double), host, ld * sizeof(double),
-                              dst.rows * sizeof(double), dst.cols, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->counters[3] += dst.rows * dst.cols * (int64_t)sizeof(double);
+// host column-major (ld) -> panel-major device block (synchronises: the caller's buffer may go away)
+inline void upload_cm_block(kr_ctx* ctx, const double* host, int64_t ld, PanelBuf& dst) {
+    const int64_t n = dst.n;
+    const int k = dst.cols;
+    if (ld < n) fail(KR_ERR_ARG, "leading dimension smaller than the number of rows");
+    DevBuf<double> stage(ctx, (size_t)std::max<int64_t>(n * k, 1));
+    if (n > 0 && k > 0) {
+        KR_CUDA(cudaMemcpy2DAsync(stage.p, n * sizeof(double), host, ld * sizeof(double), n * sizeof(double), k,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        ctx->counters[3] += n * k * (int64_t)sizeof(double);
+    }
+    cm_to_panel(ctx, stage.p, n, dst);
     KR_CUDA(cudaStreamSynchronize(ctx->stream));
 }
-inline void download_cm_to_host(kr_ctx* ctx, const double* dev, int64_t rows, int64_t cols, double* host, int64_t ld) {
-    if (rows == 0 || cols == 0) return;
-    KR_CUDA(cudaMemcpy2DAsync(host, ld * sizeof(double), dev, rows * sizeof(double), rows * sizeof(double), cols,
-                              cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->counters[4] += rows * cols * (int64_t)sizeof(double);
+// panel-major device block -> host column-major, columns [0, cols)
+inline void download_cm_block(kr_ctx* ctx, const PanelBuf& src, double* host, int64_t ld, int cols = -1) {
+    const int64_t n = src.n;
+    const int k = cols < 0 ? src.cols : std::min(cols, src.cols);
+    if (ld < n) fail(KR_ERR_ARG, "leading dimension smaller than the number of rows");
+    DevBuf<double> stage(ctx, (size_t)std::max<int64_t>(n * src.cols, 1));
+    panel_to_cm(ctx, src, stage.p, n);
+    if (n > 0 && k > 0) {
+        KR_CUDA(cudaMemcpy2DAsync(host, ld * sizeof(double), stage.p, n * sizeof(double), n * sizeof(double), k,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->counters[4] += n * k * (int64_t)sizeof(double);
+    }
     KR_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-// C(m x n) = alpha * op(A) * op(B) + beta * C   (device, column-major)
-inline void gemm(kr_ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                 int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
-    if (m == 0 || n == 0) return;
-    KR_CUBLAS(cublasDgemm(ctx->cublas, ta ? CUBLAS_OP_T : CUBLAS_OP_N, tb ? CUBLAS_OP_T : CUBLAS_OP_N, (int)m, (int)n,
-                          (int)k, &alpha, A, (int)lda, B, (int)ldb, &beta, C, (int)ldc));
-    ctx->counters[0] += 1;
-}
-
-// ------------------------------------------------------------------ FP64 tensor-core Gram
-// G = V' W for tall-skinny column-major blocks (V: n x c, W: n x b, b <= 128): the CGS2 / third-pass
-// Gram of functions/lanczos_krylov.m:110-112 and functions/arnoldi_krylov.m:104,120-122 when the block
-// width makes it a real dense contraction.  DMMA m8n8k4 (the only fp64 tensor shape family on sm_100;
-// tcgen05 has no fp64 kind): the A fragment is a 8x4 tile of V' and the B fragment a 4x8 tile of W,
-// both read straight from global memory - 4 consecutive rows of 8 columns = 8 fully used 32-byte
-// sectors per warp load, so no shared-memory staging is needed.  grid = (row chunks, ceil(c/32)); a
-// CTA owns a 32 x b tile of G for its chunk of rows, warp w owns the 8-column tiles w and w+8.
-// Split-K partials land in a fixed layout and are summed in a fixed order (deterministic).
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-constexpr int GRAM_KCH = 4096;     // rows per CTA
-__global__ void __launch_bounds__(256)
-gram_dmma_kernel(const double* __restrict__ V, int64_t ldv, int c, const double* __restrict__ W, int64_t ldw,
-                 int b, int64_t n, double* __restrict__ partial) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kk = lane & 3, idx = lane >> 2;
-    const int m0 = blockIdx.y * 32;
-    const int64_t r0 = (int64_t)blockIdx.x * GRAM_KCH, r1 = min(n, r0 + (int64_t)GRAM_KCH);
-    const int ntiles = (b + 7) >> 3;
-    double acc[4][2][2];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int s = 0; s < 2; ++s) acc[mt][s][0] = acc[mt][s][1] = 0.0;
-    const bool has0 = warp < ntiles, has1 = warp + 8 < ntiles;     // warp-uniform
-    if (has0) {
-        for (int64_t k0 = r0; k0 < r1; k0 += 4) {
-            const int64_t row = k0 + kk;
-            const bool rok = row < r1;
-            double a[4];
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
-                const int col = m0 + mt * 8 + idx;
-                a[mt] = (rok && col < c) ? __ldg(V + row + (int64_t)col * ldv) : 0.0;
-            }
-            {
-                const int col = warp * 8 + idx;
-                const double bb = (rok && col < b) ? __ldg(W + row + (int64_t)col * ldw) : 0.0;
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][0][0], acc[mt][0][1], a[mt], bb);
-            }
-            if (has1) {
-                const int col = (warp + 8) * 8 + idx;
-                const double bb = (rok && col < b) ? __ldg(W + row + (int64_t)col * ldw) : 0.0;
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][1][0], acc[mt][1][1], a[mt], bb);
-            }
-        }
-    }
-    // C fragment: lane holds C[idx][2*kk], C[idx][2*kk+1] of each 8x8 tile; partial is column-major c x b
-    double* out = partial + (int64_t)blockIdx.x * c * b;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const int nt = warp + s * 8;
-        if (nt >= ntiles) continue;
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-            const int m = m0 + mt * 8 + idx;
-            const int n0 = nt * 8 + 2 * kk;
-            if (m < c) {
-                if (n0 < b) out[m + (int64_t)n0 * c] = acc[mt][s][0];
-                if (n0 + 1 < b) out[m + (int64_t)(n0 + 1) * c] = acc[mt][s][1];
-            }
-        }
-    }
-}
-
-// G (c x b, column-major, device) = V' W.  Falls back to cuBLAS for b > 128.
-inline void gemm(kr_ctx* ctx, bool ta, bool tb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                 int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
-inline void gram_tn(kr_ctx* ctx, const double* V, int64_t ldv, int64_t c, const double* W, int64_t ldw, int64_t b,
-                    int64_t n, double* G) {
-    if (c == 0 || b == 0) return;
-    static const bool force_cublas = getenv("KR_GRAM_CUBLAS") != nullptr;   // A/B switch for debugging
-    if (b > 128 || force_cublas) {
-        gemm(ctx, true, false, c, b, n, 1.0, V, ldv, W, ldw, 0.0, G, c);
-        return;
-    }
-    const int chunks = (int)ceil_div(n, GRAM_KCH);
-    DevBuf<double> partial(ctx, (size_t)chunks * c * b);
-    dim3 grid((unsigned)chunks, (unsigned)ceil_div(c, 32));
-    KR_LAUNCH(ctx, gram_dmma_kernel, grid, 256, 0, V, ldv, (int)c, W, ldw, (int)b, n, partial.p);
-    sum_partials(ctx, partial.p, chunks, (int)(c * b), G);
-}
-
-// Y = A * X for column-major device blocks (n x k)
-inline void spmm_cm(kr_ctx* ctx, const kr_matrix* M, const double* X, int64_t k, double* Y) {
-    const int64_t n = M->dev.n;
-    PanelBuf xb(ctx, n, (int)k), yb(ctx, n, (int)k);
-    cm_to_panel(ctx, X, n, xb);
-    EpiPlain epi{yb.p(), xb.p(), 1.0, 0.0};
-    launch_spmm(ctx, M->dev, xb.p(), xb.panels, epi, nullptr, (int)k);
-    panel_to_cm(ctx, yb, Y, n);
-}
-
-// Thin Householder QR in place: W (n x bs) <- Q, R (bs x bs, host, upper triangular).
-inline void qr_thin(kr_ctx* ctx, double* W, int64_t n, int64_t bs, HostMat& R) {
-    R = HostMat(bs, bs);
-    if (n < bs) fail(KR_ERR_UNSUPPORTED, "thin QR needs n >= block size");
-    int lwork1 = 0, lwork2 = 0;
-    KR_CUSOLVER(cusolverDnDgeqrf_bufferSize(ctx->cusolver, (int)n, (int)bs, W, (int)n, &lwork1));
-    DevBuf<double> tau(ctx, bs);
-    KR_CUSOLVER(cusolverDnDorgqr_bufferSize(ctx->cusolver, (int)n, (int)bs, (int)bs, W, (int)n, tau.p, &lwork2));
-    const int lwork = std::max(lwork1, lwork2);
-    DevBuf<double> work(ctx, std::max(lwork, 1));
-    DevBuf<int> info(ctx, 1);
-    KR_CUSOLVER(cusolverDnDgeqrf(ctx->cusolver, (int)n, (int)bs, W, (int)n, tau.p, work.p, lwork, info.p));
-    std::vector<double> top((size_t)bs * bs);
-    // leading bs x bs of the factored W (leading dimension n): strided copy
-    KR_CUDA(cudaMemcpy2DAsync(top.data(), bs * sizeof(double), W, n * sizeof(double), bs * sizeof(double), bs,
-                              cudaMemcpyDeviceToHost, ctx->stream));
-    KR_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int64_t j = 0; j < bs; ++j)
-        for (int64_t i = 0; i <= j; ++i) R(i, j) = top[(size_t)(i + j * bs)];
-    KR_CUSOLVER(cusolverDnDorgqr(ctx->cusolver, (int)n, (int)bs, (int)bs, W, (int)n, tau.p, work.p, lwork, info.p));
-    ctx->counters[0] += 2;
-}
-
-inline double fro_norm(const HostMat& R) {
-    double s = 0;
-    for (double v : R.a) s += v * v;
-    return std::sqrt(s);
+inline bool is_symmetric(const HostMat& B) {
+    for (int64_t i = 0; i < B.rows; ++i)
+        for (int64_t j = 0; j < i; ++j)
+            if (B(i, j) != B(j, i)) return false;
+    return B.rows == B.cols;
 }
 
 // ---- host-side phase timers of the wide-block path (KR_PROFILE_WIDE=1 prints them to stderr at the end of
 // fun_update / trace_fun_update; they synchronise the stream, so they are a diagnostic, not a product path)
 struct WideProf {
     bool on = getenv("KR_PROFILE_WIDE") != nullptr;
-    double eig_small = 0, eig_large = 0, step = 0, other = 0;
-    int n_small = 0, n_large = 0, n_step = 0, max_dim = 0;
+    double step = 0, fun = 0;
+    int n_step = 0, n_fun = 0, max_dim = 0;
     static double now() {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     }
     void report(const char* what) {
         if (!on) return;
-        fprintf(stderr, "[kr wide] %s: krylov steps %d %.2f ms | eig(n<=110, smem Jacobi) %d %.2f ms | eig(syevd) %d %.2f ms "
-                        "(largest n %d)\n", what, n_step, step, n_small, eig_small, n_large, eig_large, max_dim);
-        eig_small = eig_large = step = other = 0;
-        n_small = n_large = n_step = max_dim = 0;
+        fprintf(stderr, "[kr wide] %s: krylov steps %d %.2f ms | f(Gm) evaluations %d %.2f ms (largest n %d)\n", what,
+                n_step, step, n_fun, fun, max_dim);
+        step = fun = 0;
+        n_step = n_fun = max_dim = 0;
     }
 };
 inline WideProf& wide_prof() { static WideProf p; return p; }
 
-// Vf(:, k) = V(:, k) * f(w_k)  (column-major n x n), the first half of F = V f(D) V'
-__global__ void scale_cols_fun_kernel(const double* __restrict__ V, const double* __restrict__ w, int n, int fun,
-                                      double* __restrict__ Vf) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (int64_t)n * n) return;
-    const double x = w[e / n];
-    const double fx = fun == KR_FUN_EXP ? exp(x) : fun == KR_FUN_SINH ? sinh(x) : cosh(x);
-    Vf[e] = V[e] * fx;
+// ------------------------------------------------------------------------------------ small device kernels
+__global__ void add_inplace_kernel(double* __restrict__ a, const double* __restrict__ b, int64_t total) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) a[e] += b[e];
 }
 
-inline int jacobi_max_dim() {
-    static const int v = [] { const char* e = getenv("KR_JACOBI_MAX"); return e ? atoi(e) : 16; }();
-    return v;
-}
-
-// ---- small symmetric eigen-solves on the device (host in / host out)
-// evals (ascending); if F != nullptr also F = V f(D) V'.
-inline void sym_eig_dev(kr_ctx* ctx, const HostMat& S, std::vector<double>& evals, int fun, HostMat* F) {
-    const int n = (int)S.rows;
-    evals.assign(n, 0.0);
-    if (n == 0) return;
-    WideProf& wp = wide_prof();
-    const double t_begin = wp.on ? WideProf::now() : 0.0;
-    struct Scope {
-        WideProf& wp; double t0; int n; bool small;
-        ~Scope() {
-            if (!wp.on) return;
-            const double dt = WideProf::now() - t0;
-            if (small) { wp.eig_small += dt; wp.n_small++; } else { wp.eig_large += dt; wp.n_large++; }
-            wp.max_dim = std::max(wp.max_dim, n);
+// R (bs x bs, unpadded) -> padded bpad x bpad block (upper triangle; the rest zero) and the lucky-breakdown test:
+// Lanczos ||R||_F < 1e-8 (lanczos_krylov.m:74,91); Arnoldi ||R||_2 < 1e-12 (arnoldi_krylov.m:79,100), decided by the
+// Frobenius norm where it can be (||R||_F / sqrt(bs) <= ||R||_2 <= ||R||_F) and by a power iteration on R'R otherwise.
+__global__ void __launch_bounds__(256)
+hsub_lucky_kernel(const double* __restrict__ R, int bs, int bpad, double* __restrict__ Rp, int arnoldi, int* __restrict__ lucky) {
+    __shared__ double red[256];
+    __shared__ double x[HQR_MAXB], y[HQR_MAXB];
+    double s = 0.0;
+    for (int e = threadIdx.x; e < bpad * bpad; e += 256) {
+        const int i = e % bpad, j = e / bpad;
+        double v = 0.0;
+        if (i < bs && j < bs && i <= j) v = R[i + (size_t)j * bs];
+        Rp[e] = v;
+        s += v * v;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    const double fro = sqrt(red[0]);
+    int lk;
+    if (!arnoldi) lk = fro < 1e-8;
+    else if (bs == 1) lk = fabs(R[0]) < 1e-12;
+    else if (fro / sqrt((double)bs) >= 1e-12) lk = 0;
+    else if (fro < 1e-12) lk = 1;
+    else {
+        // ||R||_2 by power iteration on R'R (bs <= 128; a rare path, right at a breakdown)
+        for (int i = threadIdx.x; i < bs; i += 256) x[i] = 1.0;
+        __syncthreads();
+        double lam = 0.0;
+        for (int itn = 0; itn < 200; ++itn) {
+            for (int i = threadIdx.x; i < bs; i += 256) {          // y = R x
+                double t = 0.0;
+                for (int j = i; j < bs; ++j) t += R[i + (size_t)j * bs] * x[j];
+                y[i] = t;
+            }
+            __syncthreads();
+            for (int j = threadIdx.x; j < bs; j += 256) {          // x = R' y
+                double t = 0.0;
+                for (int i = 0; i <= j; ++i) t += R[i + (size_t)j * bs] * y[i];
+                x[j] = t;
+            }
+            __syncthreads();
+            double nn2 = 0.0;
+            for (int j = 0; j < bs; ++j) nn2 += x[j] * x[j];       // every thread the same serial sum
+            const double nrm = sqrt(nn2);
+            lam = nrm;
+            __syncthreads();
+            if (nrm == 0.0) break;
+            for (int j = threadIdx.x; j < bs; j += 256) x[j] /= nrm;
+            __syncthreads();
         }
-    } scope{wp, t_begin, n, n <= jacobi_max_dim()};
-    DevBuf<double> dA(ctx, (size_t)n * n), dW(ctx, n);
-    dA.upload(S.a.data(), (size_t)n * n);
-    const bool vec = F != nullptr;
-    // One-CTA cyclic Jacobi only for tiny projections: measured 12-15 ms per solve at n = 100-156 against
-    // 1.7 ms for cuSOLVER syevd at n = 208 (profiles/r01_wide_block_phases.txt); it wins only below ~16-32, where
-    // syevd's fixed cost of several launches dominates.
-    if (n <= jacobi_max_dim() && jacobi_smem_bytes(n, vec) <= JAC_SMEM_LIMIT) {
-        if (!vec) {
-            static bool set1 = false;
-            if (!set1) { KR_CUDA(cudaFuncSetAttribute(eigvals_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_LIMIT)); set1 = true; }
-            KR_LAUNCH(ctx, eigvals_batched_kernel, 1, JAC_THREADS, jacobi_smem_bytes(n, false), dA.p, n, dW.p, (double*)nullptr);
-            evals = dW.to_host();
-        } else {
-            static bool set2 = false;
-            if (!set2) { KR_CUDA(cudaFuncSetAttribute(symfun_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_LIMIT)); set2 = true; }
-            DevBuf<double> dF(ctx, (size_t)n * n);
-            KR_LAUNCH(ctx, symfun_batched_kernel, 1, JAC_THREADS, jacobi_smem_bytes(n, true), dA.p, n, fun, dF.p, (double*)nullptr);
-            *F = HostMat(n, n);
-            dF.download(F->a.data(), (size_t)n * n);
-        }
-        return;
+        lk = sqrt(lam) < 1e-12;
     }
-    // large projection: cuSOLVER syevd (plain library call), then F = V f(D) V' by dgemm
-    int lwork = 0;
-    cusolverEigMode_t jobz = vec ? CUSOLVER_EIG_MODE_VECTOR : CUSOLVER_EIG_MODE_NOVECTOR;
-    KR_CUSOLVER(cusolverDnDsyevd_bufferSize(ctx->cusolver, jobz, CUBLAS_FILL_MODE_LOWER, n, dA.p, n, dW.p, &lwork));
-    DevBuf<double> work(ctx, std::max(lwork, 1));
-    DevBuf<int> info(ctx, 1);
-    KR_CUSOLVER(cusolverDnDsyevd(ctx->cusolver, jobz, CUBLAS_FILL_MODE_LOWER, n, dA.p, n, dW.p, work.p, lwork, info.p));
-    ctx->counters[0] += 1;
-    if (vec) {
-        // F = (V f(D)) V' entirely on the device: one column-scaling kernel + one dgemm, one download
-        DevBuf<double> dVf(ctx, (size_t)n * n), dF(ctx, (size_t)n * n);
-        KR_LAUNCH(ctx, scale_cols_fun_kernel, (int)ceil_div((int64_t)n * n, 256), 256, 0, dA.p, dW.p, n, fun, dVf.p);
-        gemm(ctx, false, true, n, n, n, 1.0, dVf.p, n, dA.p, n, 0.0, dF.p, n);
-        *F = HostMat(n, n);
-        KR_CUDA(cudaMemcpyAsync(evals.data(), dW.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        dF.download(F->a.data(), (size_t)n * n);
-    } else {
-        evals = dW.to_host();
+    if (threadIdx.x == 0) *lucky = lk;
+}
+
+// Assemble [tGm; Gm] (two nn x nn column-major matrices, tGm first) from the device-resident blocks of H:
+//   Gm = sym(H(1:nn, 1:nn)),  tGm = Gm + CmS (rk x rk, leading block)   (trace_fun_update.m:72-81, fun_update.m:93-104)
+struct HBlocks {
+    const double* const* hcol;   // [steps] (rows_s * bpad) x bpad
+    const double* const* hsub;   // [steps] bpad x bpad
+    int arnoldi, bs, bpad;
+};
+__device__ __forceinline__ double hblock_at(const HBlocks& H, int a, int b) {
+    const int lb = b / H.bs, ib = b % H.bs, la = a / H.bs, ia = a % H.bs;
+    if (la == lb + 1) return H.hsub[lb][ia + (size_t)ib * H.bpad];
+    if (la > lb) return 0.0;
+    int local, rows;
+    if (H.arnoldi) { local = la; rows = lb + 1; }
+    else {
+        const int first = lb > 0 ? lb - 1 : 0;
+        if (la < first) return 0.0;
+        local = la - first;
+        rows = lb > 0 ? 2 : 1;
+    }
+    return H.hcol[lb][(size_t)(local * H.bpad + ia) + (size_t)ib * rows * H.bpad];
+}
+__global__ void assemble_proj_kernel(HBlocks H, int nn, const double* __restrict__ CmS, int rk, double* __restrict__ out) {
+    const int64_t total = (int64_t)nn * nn;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int a = (int)(e % nn), b = (int)(e / nn);
+        const double g = 0.5 * (hblock_at(H, a, b) + hblock_at(H, b, a));
+        const double cm = (a < rk && b < rk) ? CmS[a + (size_t)b * rk] : 0.0;
+        out[e] = g + cm;
+        out[total + e] = g;
     }
 }
 
-// spectral norm of a symmetric host matrix = max |eigenvalue| (device eigen-solve)
-inline double sym_norm2_dev(kr_ctx* ctx, const HostMat& S) {
-    std::vector<double> ev;
-    sym_eig_dev(ctx, S, ev, KR_FUN_EXP, nullptr);
-    double m = 0;
-    for (double v : ev) m = std::max(m, std::abs(v));
-    return m;
+// D = sym(X - pad(Xold)) (nn x nn; Xold is no x no in the leading corner), partial[b] = sum of squares
+__global__ void __launch_bounds__(256)
+diff_sym_kernel(const double* __restrict__ X, int nn, const double* __restrict__ Xold, int no, double* __restrict__ D,
+                double* __restrict__ partial) {
+    __shared__ double red[256];
+    const int64_t total = (int64_t)nn * nn;
+    double s = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        const int a = (int)(e % nn), b = (int)(e / nn);
+        double v = 0.5 * (X[a + (size_t)b * nn] + X[b + (size_t)a * nn]);
+        if (a < no && b < no) v -= 0.5 * (Xold[a + (size_t)b * no] + Xold[b + (size_t)a * no]);
+        D[e] = v;
+        s += v * v;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+// info[0] = ||D||_F, need = Frobenius norm does not decide ||D||_2 < tol
+__global__ void stop_band_kernel(const double* __restrict__ partial, int count, int nn, double tol, double* __restrict__ info,
+                                 int* __restrict__ need) {
+    double s = 0.0;
+    for (int i = 0; i < count; ++i) s += partial[i];
+    const double fro = sqrt(s);
+    info[0] = fro;
+    info[1] = -1.0;
+    *need = (fro >= tol) && (fro / sqrt((double)nn) < tol);
 }
 
-inline double trace_formula_host(int fun, const std::vector<double>& d1, const std::vector<double>& d2) {
-    double s = 0;
-    for (size_t i = 0; i < d1.size(); ++i) {
-        if (fun == KR_FUN_EXP) s += std::exp(d1[i]) * (1.0 - std::exp(d2[i] - d1[i]));
-        else if (fun == KR_FUN_SINH) s += std::sinh(d1[i]) - std::sinh(d2[i]);
-        else s += std::cosh(d1[i]) - std::cosh(d2[i]);
+// rows of the basis at the given nodes: Ra (k x dim, column-major) with Ra(a, blk*bs + c) = Um_blk(node_a, c)
+struct BlockPtrs { const double* p[TS_MAXP]; };      // one pointer per BLOCK (panel 0 of the block)
+__global__ void gather_basis_rows_kernel(BlockPtrs B, int nblocks, int bs, int64_t n, const int64_t* __restrict__ nodes, int k,
+                                         int dim, double* __restrict__ Ra) {
+    const int64_t total = (int64_t)k * dim;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int a = (int)(e % k), col = (int)(e / k);
+        const int blk = col / bs, c = col % bs;
+        double v = 0.0;
+        if (blk < nblocks) v = B.p[blk][(int64_t)(c / PW) * n * PW + (nodes[a] - 1) * PW + (c % PW)];
+        Ra[e] = v;
     }
-    return s;
+}
+// s[q] = sum_b T(i1[q], b) * Ra(i2[q], b)      (one warp per q)
+__global__ void bilinear_rows_kernel(const double* __restrict__ T, const double* __restrict__ Ra, int k, int dim,
+                                     const int* __restrict__ i1, const int* __restrict__ i2, int nq, double* __restrict__ s) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    double acc = 0.0;
+    for (int b = lane; b < dim; b += 32) acc += T[i1[q] + (size_t)b * k] * Ra[i2[q] + (size_t)b * k];
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) s[q] = acc;
+}
+// out[q] = X(i1[q], i2[q]) of an n x n column-major matrix
+__global__ void gather_entries_kernel(const double* __restrict__ X, int64_t n, const int64_t* __restrict__ i1,
+                                      const int64_t* __restrict__ i2, int nq, double* __restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) out[q] = X[(i1[q] - 1) + (i2[q] - 1) * n];
 }
 
 }  // namespace kr
@@ -320,154 +252,215 @@ struct kr_krylov {
     const kr_matrix* A = nullptr;
     bool arnoldi = false;
     int64_t n = 0, bs = 0, steps = 0;
-    kr::CmMat V;            // Lanczos: n x (bs or 2bs) window; Arnoldi: n x (steps+1)*bs (capacity grows)
-    int64_t vcols = 0;
-    kr::HostMat H, K;
-    bool lucky = false;
+    int bp = 0, bpad = 0;                                   // panels per block, padded block width
+    std::vector<std::unique_ptr<kr::PanelBuf>> V;           // Lanczos: the last <= 2 blocks; Arnoldi: all blocks
+    std::vector<kr::DevBuf<double>> hcol, hsub;             // per step: CGS2 coefficients vs the retained blocks; R
+    std::vector<int> hrows;                                 // blocks in hcol[s]
+    kr::DevBuf<int> lucky_dev;
+    kr::DevBuf<const double*> hcol_ptr, hsub_ptr;           // device copies of the block pointers (grown as needed)
+    std::vector<const double*> hcol_host, hsub_host;        // their host staging (must outlive the async copies)
+    kr::HqrWork qr;
+    kr::DevBuf<double> scratch, h1;
+    bool lucky = false;                                     // valid after sync_lucky()
+    int64_t vcols() const { return (int64_t)V.size() * bs; }
+    kr::HBlocks hblocks() const {
+        kr::HBlocks H;
+        H.hcol = hcol_ptr.p; H.hsub = hsub_ptr.p; H.arnoldi = arnoldi; H.bs = (int)bs; H.bpad = bpad;
+        return H;
+    }
 };
 
 namespace kr {
 
-// one add_inf_pole step (lanczos_krylov.m:73-101 / arnoldi_krylov.m:78-111); the continuation
-// block params.last is always the last bs columns of V.
-inline void krylov_step(kr_krylov* st) {
-    kr_ctx* ctx = st->ctx;
-    const int64_t n = st->n, bs = st->bs, c = st->vcols;
-    CmMat W(ctx, n, bs);
-    spmm_cm(ctx, st->A, st->V.col(c - bs), bs, W.p());
-    // CGS2 against V (n x c)
-    DevBuf<double> dh(ctx, (size_t)c * bs), dh1(ctx, (size_t)c * bs);
-    gram_tn(ctx, st->V.p(), n, c, W.p(), n, bs, n, dh.p);
-    gemm(ctx, false, false, n, bs, c, -1.0, st->V.p(), n, dh.p, c, 1.0, W.p(), n);
-    gram_tn(ctx, st->V.p(), n, c, W.p(), n, bs, n, dh1.p);
-    gemm(ctx, false, false, n, bs, c, -1.0, st->V.p(), n, dh1.p, c, 1.0, W.p(), n);
-    std::vector<double> h = dh.to_host(), h1 = dh1.to_host();
-    for (size_t i = 0; i < h.size(); ++i) h[i] += h1[i];
-    HostMat& H = st->H;
-    H.grow(H.rows + bs, H.cols + bs);
-    const int64_t R = H.rows, C = H.cols;
-    HostMat Rf;
-    if (!st->arnoldi) {
-        const int64_t r0 = std::max<int64_t>(1, R - 3 * bs + 1) - 1;      // lanczos_krylov.m:88
-        for (int64_t j = 0; j < bs; ++j)
-            for (int64_t i = 0; i < c; ++i) H(r0 + i, C - bs + j) = h[(size_t)(i + j * c)];
-        qr_thin(ctx, W.p(), n, bs, Rf);
-        for (int64_t j = 0; j < bs; ++j)
-            for (int64_t i = 0; i < bs; ++i) H(R - bs + i, C - bs + j) = Rf(i, j);
-        st->lucky = fro_norm(Rf) < 1e-8;                                   // :91
-        if (c == bs) {                                                     // :94-99
-            CmMat Vn(ctx, n, 2 * bs);
-            KR_CUDA(cudaMemcpyAsync(Vn.p(), st->V.p(), (size_t)n * bs * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-            KR_CUDA(cudaMemcpyAsync(Vn.col(bs), W.p(), (size_t)n * bs * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-            st->V = std::move(Vn);
-            st->vcols = 2 * bs;
-        } else {
-            KR_CUDA(cudaMemcpyAsync(st->V.p(), st->V.col(bs), (size_t)n * bs * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-            KR_CUDA(cudaMemcpyAsync(st->V.col(bs), W.p(), (size_t)n * bs * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        }
-    } else {
-        HostMat& K = st->K;
-        K.grow(K.rows + bs, K.cols + bs);
-        for (int64_t j = 0; j < bs; ++j)
-            for (int64_t i = 0; i < c; ++i) H(i, C - bs + j) = h[(size_t)(i + j * c)];     // arnoldi_krylov.m:96
-        for (int64_t i = 0; i < bs; ++i) K(R - 2 * bs + i, C - bs + i) = 1.0;              // :97
-        qr_thin(ctx, W.p(), n, bs, Rf);
-        // ||r||_2 < 1e-12 (:100): spectral norm of a bs x bs triangular matrix = sqrt(max eig(R'R))
-        {
-            HostMat RtR(bs, bs);
-            for (int64_t i = 0; i < bs; ++i)
-                for (int64_t j = 0; j < bs; ++j) {
-                    double s = 0;
-                    for (int64_t k = 0; k < bs; ++k) s += Rf(k, i) * Rf(k, j);
-                    RtR(i, j) = s;
-                }
-            // ||R||_F / sqrt(bs) <= ||R||_2 <= ||R||_F: away from breakdown the Frobenius norm already decides
-            // and the bs x bs eigen-solve (one more device round trip per step) is skipped
-            const double fro = fro_norm(Rf);
-            if (bs == 1) st->lucky = std::abs(Rf(0, 0)) < 1e-12;
-            else if (fro / std::sqrt((double)bs) >= 1e-12) st->lucky = false;
-            else if (fro < 1e-12) st->lucky = true;
-            else st->lucky = std::sqrt(sym_norm2_dev(ctx, RtR)) < 1e-12;
-        }
-        // third reorthogonalisation (:104-106)
-        DevBuf<double> dhh(ctx, (size_t)c * bs);
-        gram_tn(ctx, st->V.p(), n, c, W.p(), n, bs, n, dhh.p);
-        gemm(ctx, false, false, n, bs, c, -1.0, st->V.p(), n, dhh.p, c, 1.0, W.p(), n);
-        std::vector<double> hh = dhh.to_host();
-        for (int64_t j = 0; j < bs; ++j)
-            for (int64_t i = 0; i < c; ++i) {
-                double s = 0;
-                for (int64_t k = 0; k < bs; ++k) s += hh[(size_t)(i + k * c)] * Rf(k, j);
-                H(i, C - bs + j) += s;
-            }
-        for (int64_t j = 0; j < bs; ++j)
-            for (int64_t i = 0; i < bs; ++i) H(R - bs + i, C - bs + j) = Rf(i, j);
-        // V = [V, w]
-        if ((c + bs) * n > (int64_t)st->V.buf.count) {
-            CmMat Vn(ctx, n, std::max<int64_t>(2 * (c + bs), 8 * bs));
-            KR_CUDA(cudaMemcpyAsync(Vn.p(), st->V.p(), (size_t)n * c * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-            st->V = std::move(Vn);
-        }
-        KR_CUDA(cudaMemcpyAsync(st->V.col(c), W.p(), (size_t)n * bs * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        st->vcols = c + bs;
-    }
-    st->steps += 1;
-    KR_CUDA(cudaStreamSynchronize(ctx->stream));
+inline PanelList list_of(const std::vector<std::unique_ptr<PanelBuf>>& V) {
+    PanelList l;
+    for (auto& b : V) l.add(*b);
+    return l;
+}
+inline PanelList list_of(const PanelBuf& b) {
+    PanelList l;
+    l.add(b);
+    return l;
 }
 
-// start: V1 = qr(b, 0), one step    (lanczos_krylov.m:30-58, arnoldi_krylov.m:32-62); b on the device
-inline std::unique_ptr<kr_krylov> krylov_start(kr_ctx* ctx, const kr_matrix* A, bool arnoldi, int64_t bs, CmMat&& b) {
+inline void krylov_publish_pointers(kr_krylov* st) {
+    kr_ctx* ctx = st->ctx;
+    const size_t s = st->hcol.size();
+    if (st->hcol_ptr.count < s) {
+        const size_t cap = std::max<size_t>(16, 2 * s);
+        st->hcol_ptr.reset(ctx, cap);
+        st->hsub_ptr.reset(ctx, cap);
+    }
+    std::vector<const double*>& a = st->hcol_host;
+    std::vector<const double*>& b = st->hsub_host;
+    a.reserve(256);                                   // no reallocation while earlier copies may be in flight
+    b.reserve(256);
+    if (s > a.capacity()) KR_CUDA(cudaStreamSynchronize(ctx->stream));
+    a.resize(s);
+    b.resize(s);
+    for (size_t i = 0; i < s; ++i) { a[i] = st->hcol[i].p; b[i] = st->hsub[i].p; }
+    KR_CUDA(cudaMemcpyAsync(st->hcol_ptr.p, a.data(), s * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
+    KR_CUDA(cudaMemcpyAsync(st->hsub_ptr.p, b.data(), s * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
+}
+
+// one add_inf_pole step (lanczos_krylov.m:73-101 / arnoldi_krylov.m:78-111); the continuation
+// block params.last is always the last block of V.  Enqueues only; lucky is read back by sync_lucky().
+inline void krylov_step(kr_krylov* st) {
+    kr_ctx* ctx = st->ctx;
+    const int64_t n = st->n;
+    const int bs = (int)st->bs, bpad = st->bpad;
+    std::unique_ptr<PanelBuf> W(new PanelBuf(ctx, n, bs));
+    const PanelBuf& last = *st->V.back();
+    EpiPlain epi{W->p(), last.p(), 1.0, 0.0};
+    launch_spmm(ctx, st->A->dev, last.p(), last.panels, epi, nullptr, bs);
+    const PanelList Vl = list_of(st->V), Wl = list_of(*W);
+    const int cblocks = (int)st->V.size();
+    const size_t hsz = (size_t)cblocks * bpad * bpad;
+    st->hcol.emplace_back(ctx, hsz);
+    st->hsub.emplace_back(ctx, (size_t)bpad * bpad);
+    st->hrows.push_back(cblocks);
+    double* h = st->hcol.back().p;
+    if (st->h1.count < hsz) st->h1.reset(ctx, hsz);
+    const int eg = ew_grid(ctx, (int64_t)hsz);
+    // CGS2 against the retained blocks (lanczos_krylov.m:109-115, arnoldi_krylov.m:119-125)
+    ts_gram(ctx, Vl, Wl, n, h, st->scratch);
+    ts_update(ctx, Vl, Wl, n, h);
+    ts_gram(ctx, Vl, Wl, n, st->h1.p, st->scratch);
+    ts_update(ctx, Vl, Wl, n, st->h1.p);
+    KR_LAUNCH(ctx, add_inplace_kernel, eg, 256, 0, h, st->h1.p, (int64_t)hsz);
+    // [w, R] = qr(w, 0)
+    hqr_thin(ctx, Wl, n, bs, st->qr);
+    if (!st->lucky_dev.p) st->lucky_dev.reset(ctx, 1);
+    KR_LAUNCH(ctx, hsub_lucky_kernel, 1, 256, 0, st->qr.st.R, bs, bpad, st->hsub.back().p, (int)st->arnoldi, st->lucky_dev.p);
+    if (st->arnoldi) {
+        // third reorthogonalisation (arnoldi_krylov.m:104-106): hh = V'w; w -= V hh; H(1:end-bs, last) += hh R
+        ts_gram(ctx, Vl, Wl, n, st->h1.p, st->scratch);
+        ts_update(ctx, Vl, Wl, n, st->h1.p);
+        const int cpad = cblocks * bpad;
+        sgemm(ctx, cpad, bpad, bpad, 1.0, st->h1.p, cpad, 0, st->hsub.back().p, bpad, 0, 1.0, h, cpad, 0, 1);
+        st->V.push_back(std::move(W));
+    } else {
+        st->V.push_back(std::move(W));
+        if (st->V.size() > 2) st->V.erase(st->V.begin());                     // lanczos_krylov.m:94-99
+    }
+    st->steps += 1;
+    krylov_publish_pointers(st);
+}
+
+inline void sync_lucky(kr_krylov* st) {
+    int lk = 0;
+    KR_CUDA(cudaMemcpyAsync(&lk, st->lucky_dev.p, sizeof(int), cudaMemcpyDeviceToHost, st->ctx->stream));
+    KR_CUDA(cudaStreamSynchronize(st->ctx->stream));
+    st->lucky = lk != 0;
+}
+
+// start: V1 = qr(b, 0), one step    (lanczos_krylov.m:30-58, arnoldi_krylov.m:32-62); b is consumed
+inline std::unique_ptr<kr_krylov> krylov_start(kr_ctx* ctx, const kr_matrix* A, bool arnoldi, int64_t bs,
+                                               std::unique_ptr<PanelBuf> b) {
     const int64_t n = A->dev.n;
-    if (b.rows != n) fail(KR_ERR_ARG, "The block vector b has wrong number of rows");
+    if (b->n != n) fail(KR_ERR_ARG, "The block vector b has wrong number of rows");
     if (bs < 1) fail(KR_ERR_ARG, "empty starting block");
+    if (bs > HQR_MAXB) fail(KR_ERR_UNSUPPORTED, "block width %lld exceeds %d", (long long)bs, HQR_MAXB);
     std::unique_ptr<kr_krylov> st(new kr_krylov());
     st->ctx = ctx; st->A = A; st->arnoldi = arnoldi; st->n = n; st->bs = bs;
-    HostMat R0;
-    qr_thin(ctx, b.p(), n, bs, R0);
-    st->V = std::move(b);
-    st->vcols = bs;
-    st->H = HostMat(bs, 0);
-    st->K = HostMat(bs, 0);
+    st->bp = b->panels;
+    st->bpad = b->panels * PW;
+    hqr_thin(ctx, list_of(*b), n, (int)bs, st->qr);
+    st->V.push_back(std::move(b));
     krylov_step(st.get());
     return st;
 }
 
-// Cm = (V1' U) B (V1' U)'   (trace_fun_update.m:65-66), V1 = first bs columns at start time
-inline HostMat core_Cm(kr_ctx* ctx, const kr_krylov* st, const CmMat& U, const HostMat& B) {
-    const int64_t n = st->n, bs = st->bs;
-    DevBuf<double> dC(ctx, (size_t)bs * bs);
-    gemm(ctx, true, false, bs, bs, n, 1.0, st->V.p(), n, U.p(), n, 0.0, dC.p, bs);
-    std::vector<double> c = dC.to_host();
-    HostMat T(bs, bs), Cm(bs, bs);
-    for (int64_t i = 0; i < bs; ++i)
-        for (int64_t j = 0; j < bs; ++j) {
-            double s = 0;
-            for (int64_t k = 0; k < bs; ++k) s += c[(size_t)(i + k * bs)] * B(k, j);
-            T(i, j) = s;
-        }
-    for (int64_t i = 0; i < bs; ++i)
-        for (int64_t j = 0; j < bs; ++j) {
-            double s = 0;
-            for (int64_t k = 0; k < bs; ++k) s += T(i, k) * c[(size_t)(j + k * bs)];
-            Cm(i, j) = s;
-        }
-    return Cm;
-}
-
-inline bool is_symmetric(const HostMat& B) {
-    for (int64_t i = 0; i < B.rows; ++i)
-        for (int64_t j = 0; j < i; ++j)
-            if (B(i, j) != B(j, i)) return false;
-    return B.rows == B.cols;
-}
-
-// dense symmetric copy of A (+ U B U') for the small-n branches (host assembly, device eigen-solve)
+// dense symmetric copy of A for the small-n branches (host assembly)
 inline HostMat dense_of(const kr_matrix* M) {
     const CsrHost& H = M->host;
     HostMat D(H.n, H.n);
     for (int64_t i = 0; i < H.n; ++i)
         for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) D(i, H.col[p]) += H.val[p];
     return D;
+}
+// fAt = sym(fA + U B U')
+inline HostMat dense_updated(const HostMat& fA, int64_t rk, const double* U, int64_t ldu, const HostMat& B, bool symmetrise) {
+    const int64_t n = fA.rows;
+    HostMat fAt = fA;
+    std::vector<double> UB((size_t)n * rk, 0.0);
+    for (int64_t a = 0; a < n; ++a)
+        for (int64_t q = 0; q < rk; ++q) {
+            double s = 0;
+            for (int64_t p = 0; p < rk; ++p) s += U[a + p * ldu] * B(p, q);
+            UB[(size_t)(a + q * n)] = s;
+        }
+    for (int64_t b = 0; b < n; ++b)
+        for (int64_t q = 0; q < rk; ++q) {
+            const double u = U[b + q * ldu];
+            if (u == 0.0) continue;
+            for (int64_t a = 0; a < n; ++a) fAt(a, b) += UB[(size_t)(a + q * n)] * u;
+        }
+    if (symmetrise) {
+        HostMat S(n, n);
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t j = 0; j < n; ++j) S(i, j) = 0.5 * (fAt(i, j) + fAt(j, i));
+        return S;
+    }
+    return fAt;
+}
+inline double host_norm1(const HostMat& S) {
+    double m = 0;
+    for (int64_t j = 0; j < S.cols; ++j) {
+        double s = 0;
+        for (int64_t i = 0; i < S.rows; ++i) s += std::abs(S(i, j));
+        m = std::max(m, s);
+    }
+    return m;
+}
+
+// Shared front end of trace_fun_update / fun_update: U on the device, Krylov start, CmS = sym((V1'U) B (V1'U)')
+struct WideSetup {
+    std::unique_ptr<kr_krylov> st;
+    DevBuf<double> CmS;            // rk x rk
+    double norm_bound = 0;         // >= ||tGm||_2, ||Gm||_2
+};
+inline WideSetup wide_setup(kr_ctx* ctx, const kr_matrix* M, int64_t rk, const double* U, int64_t ldu, const HostMat& B,
+                            bool arnoldi) {
+    const int64_t n = M->dev.n;
+    WideSetup ws;
+    PanelBuf Ud(ctx, n, (int)rk);
+    upload_cm_block(ctx, U, ldu, Ud);
+    std::unique_ptr<PanelBuf> b0(new PanelBuf(ctx, n, (int)rk));
+    KR_CUDA(cudaMemcpyAsync(b0->p(), Ud.p(), (size_t)Ud.elems() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    ws.st = krylov_start(ctx, M, arnoldi, rk, std::move(b0));
+    kr_krylov* st = ws.st.get();
+    // Cm = (V1' U) B (V1' U)'   (trace_fun_update.m:65-66): V1 is the first retained block right after the start
+    const int bpad = st->bpad;
+    DevBuf<double> dC(ctx, (size_t)bpad * bpad);
+    ts_gram(ctx, list_of(*st->V.front()), list_of(Ud), n, dC.p, st->scratch);
+    std::vector<double> c = dC.to_host();            // one synchronisation per call
+    HostMat T(rk, rk), Cm(rk, rk);
+    for (int64_t i = 0; i < rk; ++i)
+        for (int64_t j = 0; j < rk; ++j) {
+            double s = 0;
+            for (int64_t k = 0; k < rk; ++k) s += c[(size_t)(i + k * bpad)] * B(k, j);
+            T(i, j) = s;
+        }
+    for (int64_t i = 0; i < rk; ++i)
+        for (int64_t j = 0; j < rk; ++j) {
+            double s = 0;
+            for (int64_t k = 0; k < rk; ++k) s += T(i, k) * c[(size_t)(j + k * bpad)];
+            Cm(i, j) = s;
+        }
+    std::vector<double> cs((size_t)rk * rk);
+    double fro = 0;
+    for (int64_t i = 0; i < rk; ++i)
+        for (int64_t j = 0; j < rk; ++j) {
+            const double v = 0.5 * (Cm(i, j) + Cm(j, i));
+            cs[(size_t)(i + j * rk)] = v;
+            fro += v * v;
+        }
+    ws.CmS.reset(ctx, (size_t)rk * rk);
+    ws.CmS.upload(cs.data(), cs.size());
+    KR_CUDA(cudaStreamSynchronize(ctx->stream));
+    ws.norm_bound = M->norm1 + std::sqrt(fro);        // ||Gm||_2 <= ||A||_2 <= ||A||_1 (A symmetric)
+    return ws;
 }
 
 struct TfuResult { double Xm = 0; int64_t iter = 0; int lucky = 0; };
@@ -478,60 +471,41 @@ inline TfuResult trace_fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64
     const int64_t n = M->dev.n;
     TfuResult out;
     if (!is_symmetric(B)) fail(KR_ERR_UNSUPPORTED, "trace_fun_update: the device path needs a symmetric (Hermitian) B");
+    ExpmWork ew;
+    DevBuf<double> xm(ctx, 1);
     if (n <= 130) {                                           // :37-51 dense branch
-        HostMat fA = dense_of(M), fAt = fA;
-        // fAt = fA + U B U', symmetrised
-        std::vector<double> UB((size_t)n * rk, 0.0);
+        const HostMat fA = dense_of(M);
+        const HostMat S = dense_updated(fA, rk, U, ldu, B, true);
+        std::vector<double> both((size_t)2 * n * n);
+        std::copy(S.a.begin(), S.a.end(), both.begin());
         for (int64_t i = 0; i < n; ++i)
-            for (int64_t j = 0; j < rk; ++j) {
-                double s = 0;
-                for (int64_t k = 0; k < rk; ++k) s += U[i + k * ldu] * B(k, j);
-                UB[(size_t)(i + j * n)] = s;
-            }
-        for (int64_t i = 0; i < n; ++i)
-            for (int64_t j = 0; j < n; ++j) {
-                double s = 0;
-                for (int64_t k = 0; k < rk; ++k) s += UB[(size_t)(i + k * n)] * U[j + k * ldu];
-                fAt(i, j) += s;
-            }
-        HostMat S(n, n);
-        for (int64_t i = 0; i < n; ++i)
-            for (int64_t j = 0; j < n; ++j) S(i, j) = 0.5 * (fAt(i, j) + fAt(j, i));
-        std::vector<double> d1, d2;
-        sym_eig_dev(ctx, S, d1, fun, nullptr);
-        sym_eig_dev(ctx, fA, d2, fun, nullptr);
-        out.Xm = trace_formula_host(fun, d1, d2);
+            for (int64_t j = 0; j < n; ++j) both[(size_t)(n * n + i + j * n)] = 0.5 * (fA(i, j) + fA(j, i));
+        DevBuf<double> dS(ctx, both.size()), dF(ctx, both.size());
+        dS.upload(both.data(), both.size());
+        symfun_batched(ctx, dS.p, (int)n, 2, fun, std::max(host_norm1(S), host_norm1(fA)), dF.p, ew);
+        KR_LAUNCH(ctx, trace_diff_kernel, 1, 256, 0, dF.p, dF.p + n * n, (int)n, xm.p);
+        xm.download(&out.Xm, 1);
         return out;
     }
-    CmMat Ud(ctx, n, rk), b0(ctx, n, rk);
-    upload_host_cm(ctx, U, ldu, Ud);
-    KR_CUDA(cudaMemcpyAsync(b0.p(), Ud.p(), (size_t)n * rk * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    std::unique_ptr<kr_krylov> st;
-    HostMat Cm;
+    WideSetup ws = wide_setup(ctx, M, rk, U, ldu, B, false);
+    kr_krylov* st = ws.st.get();
     double Xstop[2] = {0, 0};
     int64_t j = 0;
+    DevBuf<double> SG, F;
     for (j = 1; j <= it; ++j) {
-        if (j == 1) {
-            st = krylov_start(ctx, M, false, rk, std::move(b0));
-            Cm = core_Cm(ctx, st.get(), Ud, B);
-        } else {
-            const double t0 = wide_prof().on ? WideProf::now() : 0.0;
-            krylov_step(st.get());
-            if (wide_prof().on) { KR_CUDA(cudaStreamSynchronize(ctx->stream)); wide_prof().step += WideProf::now() - t0; wide_prof().n_step++; }
-        }
-        const int64_t nn = st->H.rows - rk;
-        HostMat G(nn, nn), tG(nn, nn);
-        for (int64_t a = 0; a < nn; ++a)
-            for (int64_t b = 0; b < nn; ++b) {
-                double g = 0.5 * (st->H(a, b) + st->H(b, a));
-                double cm = (a < rk && b < rk) ? 0.5 * (Cm(a, b) + Cm(b, a)) : 0.0;
-                G(a, b) = g;
-                tG(a, b) = g + cm;
-            }
-        std::vector<double> d1, d2;
-        sym_eig_dev(ctx, tG, d1, fun, nullptr);
-        sym_eig_dev(ctx, G, d2, fun, nullptr);
-        out.Xm = trace_formula_host(fun, d1, d2);
+        const double t0 = wide_prof().on ? WideProf::now() : 0.0;
+        if (j > 1) krylov_step(st);
+        if (wide_prof().on) { KR_CUDA(cudaStreamSynchronize(ctx->stream)); wide_prof().step += WideProf::now() - t0; wide_prof().n_step++; }
+        const int nn = (int)(j * rk);
+        const size_t sz = (size_t)2 * nn * nn;
+        if (SG.count < sz) { SG.reset(ctx, sz); F.reset(ctx, sz); }
+        const double t1 = wide_prof().on ? WideProf::now() : 0.0;
+        KR_LAUNCH(ctx, assemble_proj_kernel, ew_grid(ctx, (int64_t)nn * nn), 256, 0, st->hblocks(), nn, ws.CmS.p, (int)rk, SG.p);
+        symfun_batched(ctx, SG.p, nn, 2, fun, ws.norm_bound, F.p, ew);
+        KR_LAUNCH(ctx, trace_diff_kernel, 1, 256, 0, F.p, F.p + (size_t)nn * nn, nn, xm.p);
+        KR_CUDA(cudaMemcpyAsync(&out.Xm, xm.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        sync_lucky(st);                                       // the step's only synchronisation
+        if (wide_prof().on) { wide_prof().fun += WideProf::now() - t1; wide_prof().n_fun++; wide_prof().max_dim = std::max(wide_prof().max_dim, nn); }
         out.lucky = st->lucky;
         bool done = false;
         if (j <= 2) Xstop[j - 1] = out.Xm;
@@ -548,11 +522,11 @@ inline TfuResult trace_fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64
 
 }  // namespace kr
 
-// result of the last fun_update kept until fetched
+// result of the last fun_update kept on the device until fetched
 struct FunUpdateResult {
-    kr::HostMat Xm;
-    kr::CmMat Um;           // n x dim (device)
-    int64_t n = 0, dim = 0;
+    kr::DevBuf<double> Xm;                                  // dim x dim column-major
+    std::vector<std::unique_ptr<kr::PanelBuf>> Um;          // basis blocks (bs columns each)
+    int64_t n = 0, dim = 0, bs = 0;
     bool identity_basis = false;
     bool has_basis = false;
 };
@@ -567,133 +541,210 @@ inline FuInfo fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64_t rk, co
                                  FunUpdateResult& res) {
     const int64_t n = M->dev.n;
     FuInfo info;
-    const bool herm = is_symmetric(B);
-    if (!herm) fail(KR_ERR_UNSUPPORTED, "fun_update: the device path needs a symmetric (Hermitian) B");
-    CmMat Ud(ctx, n, rk), b0(ctx, n, rk);
-    upload_host_cm(ctx, U, ldu, Ud);
-    KR_CUDA(cudaMemcpyAsync(b0.p(), Ud.p(), (size_t)n * rk * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    std::unique_ptr<kr_krylov> st;
-    HostMat Cm, Xm;
-    std::vector<HostMat> Xstop;
+    if (!is_symmetric(B)) fail(KR_ERR_UNSUPPORTED, "fun_update: the device path needs a symmetric (Hermitian) B");
+    ExpmWork ew;
+    WideSetup ws = wide_setup(ctx, M, rk, U, ldu, B, want_basis);
+    kr_krylov* st = ws.st.get();
+    std::vector<DevBuf<double>> Xs;                            // Xm of every step (the lag-2 test needs j-2)
+    std::vector<int> Xdim;
+    DevBuf<double> SG, F, D, part(ctx, 256), info_dev(ctx, 2), Q;
+    DevBuf<int> need(ctx, 1);
     int64_t j = 0;
     for (j = 1; j <= it; ++j) {
-        if (j == 1) {
-            st = krylov_start(ctx, M, want_basis, rk, std::move(b0));
-            Cm = core_Cm(ctx, st.get(), Ud, B);
-        } else {
-            const double t0 = wide_prof().on ? WideProf::now() : 0.0;
-            krylov_step(st.get());
-            if (wide_prof().on) { KR_CUDA(cudaStreamSynchronize(ctx->stream)); wide_prof().step += WideProf::now() - t0; wide_prof().n_step++; }
-        }
-        if (want_basis && 2 * st->vcols >= n) {     // :85-90 dense fallback
-            HostMat fA = dense_of(M), fAt = fA;
-            std::vector<double> UB((size_t)n * rk, 0.0);
-            for (int64_t a = 0; a < n; ++a)
-                for (int64_t q = 0; q < rk; ++q) {
-                    double s = 0;
-                    for (int64_t p = 0; p < rk; ++p) s += U[a + p * ldu] * B(p, q);
-                    UB[(size_t)(a + q * n)] = s;
-                }
-            for (int64_t b = 0; b < n; ++b)
-                for (int64_t q = 0; q < rk; ++q) {
-                    const double u = U[b + q * ldu];
-                    if (u == 0.0) continue;
-                    for (int64_t a = 0; a < n; ++a) fAt(a, b) += UB[(size_t)(a + q * n)] * u;
-                }
-            std::vector<double> ev;
-            HostMat F1, F0;
-            sym_eig_dev(ctx, fAt, ev, fun, &F1);
-            sym_eig_dev(ctx, fA, ev, fun, &F0);
-            Xm = HostMat(n, n);
-            for (size_t e = 0; e < Xm.a.size(); ++e) Xm.a[e] = F1.a[e] - F0.a[e];
-            res.Xm = Xm;
-            res.n = n; res.dim = n; res.identity_basis = true; res.has_basis = true;
+        const double t0 = wide_prof().on ? WideProf::now() : 0.0;
+        if (j > 1) krylov_step(st);
+        if (wide_prof().on) { KR_CUDA(cudaStreamSynchronize(ctx->stream)); wide_prof().step += WideProf::now() - t0; wide_prof().n_step++; }
+        if (want_basis && 2 * st->vcols() >= n) {               // :85-90 dense fallback
+            sync_lucky(st);
+            const HostMat fA = dense_of(M);
+            const HostMat fAt = dense_updated(fA, rk, U, ldu, B, false);
+            std::vector<double> both((size_t)2 * n * n);
+            std::copy(fAt.a.begin(), fAt.a.end(), both.begin());
+            std::copy(fA.a.begin(), fA.a.end(), both.begin() + (size_t)n * n);
+            DevBuf<double> dS(ctx, both.size()), dF(ctx, both.size());
+            dS.upload(both.data(), both.size());
+            symfun_batched(ctx, dS.p, (int)n, 2, fun, std::max(host_norm1(fAt), host_norm1(fA)), dF.p, ew);
+            res.Xm.reset(ctx, (size_t)n * n);
+            KR_LAUNCH(ctx, axpby_kernel, ew_grid(ctx, n * n), 256, 0, res.Xm.p, 1.0, dF.p, -1.0, dF.p + (size_t)n * n, n * n);
+            KR_CUDA(cudaStreamSynchronize(ctx->stream));
+            res.n = n; res.dim = n; res.bs = rk; res.identity_basis = true; res.has_basis = true;
             info.dim = n; info.iter = j; info.lucky = st->lucky; info.dense_fallback = 1;
             return info;
         }
-        const int64_t nn = st->H.rows - rk;
-        HostMat G(nn, nn), tG(nn, nn);
-        for (int64_t a = 0; a < nn; ++a)
-            for (int64_t b = 0; b < nn; ++b) {
-                double g = 0.5 * (st->H(a, b) + st->H(b, a));                  // :94
-                double cm = (a < rk && b < rk) ? 0.5 * (Cm(a, b) + Cm(b, a)) : 0.0;
-                G(a, b) = g;
-                tG(a, b) = g + cm;
-            }
-        std::vector<double> ev;
-        HostMat F1, F0;
-        sym_eig_dev(ctx, tG, ev, fun, &F1);
-        sym_eig_dev(ctx, G, ev, fun, &F0);
-        Xm = HostMat(nn, nn);
-        for (size_t e = 0; e < Xm.a.size(); ++e) Xm.a[e] = F1.a[e] - F0.a[e];   // :106
+        const int nn = (int)(j * rk);
+        const size_t sz = (size_t)nn * nn;
+        if (SG.count < 2 * sz) { SG.reset(ctx, 2 * sz); F.reset(ctx, 2 * sz); D.reset(ctx, sz); }
+        const double t1 = wide_prof().on ? WideProf::now() : 0.0;
+        KR_LAUNCH(ctx, assemble_proj_kernel, ew_grid(ctx, (int64_t)sz), 256, 0, st->hblocks(), nn, ws.CmS.p, (int)rk, SG.p);
+        symfun_batched(ctx, SG.p, nn, 2, fun, ws.norm_bound, F.p, ew);
+        Xs.emplace_back(ctx, sz);
+        Xdim.push_back(nn);
+        KR_LAUNCH(ctx, axpby_kernel, ew_grid(ctx, (int64_t)sz), 256, 0, Xs.back().p, 1.0, F.p, -1.0, F.p + sz, (int64_t)sz);   // :106
+        double hinfo[2] = {0, 0};
+        int hneed = 0;
+        if (j > 2) {
+            // || Xm - pad(Xm(j-2)) ||_2 < tol   (:112-114): Frobenius norm first, Lanczos only inside the band
+            const int ctas = (int)std::min<int64_t>(256, std::max<int64_t>(1, ceil_div((int64_t)sz, 256)));
+            KR_LAUNCH(ctx, diff_sym_kernel, ctas, 256, 0, Xs.back().p, nn, Xs[Xs.size() - 3].p, Xdim[Xdim.size() - 3], D.p, part.p);
+            KR_LAUNCH(ctx, stop_band_kernel, 1, 1, 0, part.p, ctas, nn, tol, info_dev.p, need.p);
+            if (Q.count < (size_t)nn * (NRM2_STEPS + 1)) Q.reset(ctx, (size_t)nn * (NRM2_STEPS + 1));
+            KR_LAUNCH(ctx, sym_norm2_kernel, 1, 256, 0, D.p, nn, Q.p, need.p, info_dev.p + 1);
+            KR_CUDA(cudaMemcpyAsync(hinfo, info_dev.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            KR_CUDA(cudaMemcpyAsync(&hneed, need.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        sync_lucky(st);                                       // the step's only synchronisation
+        if (wide_prof().on) { wide_prof().fun += WideProf::now() - t1; wide_prof().n_fun++; wide_prof().max_dim = std::max(wide_prof().max_dim, nn); }
         info.lucky = st->lucky;
         bool done = false;
-        if (j <= 2) Xstop.push_back(Xm);
-        else {
-            HostMat D = Xm;                                                      // Xm - pad(Xstop{1})
-            for (int64_t a = 0; a < Xstop[0].rows; ++a)
-                for (int64_t b = 0; b < Xstop[0].cols; ++b) D(a, b) -= Xstop[0](a, b);
-            // symmetric difference: ||.||_2 = max |eig|
-            HostMat Ds(nn, nn);
-            for (int64_t a = 0; a < nn; ++a)
-                for (int64_t b = 0; b < nn; ++b) Ds(a, b) = 0.5 * (D(a, b) + D(b, a));
-            if (sym_norm2_dev(ctx, Ds) < tol) done = true;
-            else { Xstop[0] = Xstop[1]; Xstop[1] = Xm; }
+        if (j > 2) {
+            const double err = hneed ? hinfo[1] : hinfo[0];      // inside the band the 2-norm, else the Frobenius bound decides
+            done = hneed ? (err < tol) : (hinfo[0] < tol);
         }
         if (done || st->lucky) break;
+        if (Xs.size() > 3) { Xs.erase(Xs.begin()); Xdim.erase(Xdim.begin()); }
     }
     info.iter = std::min(j, it);
-    info.dim = Xm.rows;
-    res.Xm = Xm;
+    info.dim = Xdim.back();
+    res.Xm = std::move(Xs.back());
     res.n = n;
-    res.dim = Xm.rows;
+    res.dim = Xdim.back();
+    res.bs = rk;
     res.identity_basis = false;
     res.has_basis = true;
     // Um(:, 1:size(Xm,1))  (:137) - for Lanczos this is the 2-block window, as in the reference
-    const int64_t keep = std::min<int64_t>(st->vcols, Xm.rows);
-    res.Um = CmMat(ctx, n, Xm.rows);
-    res.Um.buf.zero();
-    KR_CUDA(cudaMemcpyAsync(res.Um.p(), st->V.p(), (size_t)n * keep * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    res.Um = std::move(st->V);
     KR_CUDA(cudaStreamSynchronize(ctx->stream));
     wide_prof().report("fun_update");
     return info;
 }
 
+// ------------------------------------------------------------------------------------ normest
+// One CTA runs MATLAB's normest(S, tol) entirely on the device when the matrix is small (the reference's graphs):
+// power iteration on S'S from the column abs-sums, data-dependent stopping test included - one launch, no host
+// round trip per iteration.  S = A (symmetric) or general with the transpose supplied.
+__global__ void __launch_bounds__(1024)
+normest_small_kernel(CsrDevView A, CsrDevView At, double tol, double* __restrict__ x, double* __restrict__ sx,
+                     double* __restrict__ out /* e, cnt */) {
+    __shared__ double red[32];
+    __shared__ double s_val;
+    const int n = A.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto bsum = [&](double v) -> double {
+        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 32; ++w) s += red[w];
+            s_val = s;
+        }
+        __syncthreads();
+        return s_val;
+    };
+    auto spmv_cta = [&](const CsrDevView& S, const double* in, double* o) {
+        for (int g = warp; g < n; g += 32) {                    // one warp per stored row
+            const int p0 = S.row_ptr[g], p1 = S.row_ptr[g + 1];
+            double s = 0.0;
+            for (int p = p0 + lane; p < p1; p += 32) s += (S.val ? S.val[p] : S.uval) * in[S.col[p]];
+            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) o[S.row_order[g]] = s;
+        }
+        __syncthreads();
+    };
+    // x = sum(abs(S), 1)' = abs-sums of the columns of S = row abs-sums of S'
+    for (int g = warp; g < n; g += 32) {
+        const int p0 = At.row_ptr[g], p1 = At.row_ptr[g + 1];
+        double s = 0.0;
+        for (int p = p0 + lane; p < p1; p += 32) s += fabs(At.val ? At.val[p] : At.uval);
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) x[At.row_order[g]] = s;
+    }
+    __syncthreads();
+    double a = 0.0;
+    for (int i = tid; i < n; i += 1024) a += x[i] * x[i];
+    double e = sqrt(bsum(a));
+    double cnt = 0.0;
+    if (e == 0.0) {
+        if (tid == 0) { out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; }
+        return;
+    }
+    for (int i = tid; i < n; i += 1024) x[i] /= e;
+    __syncthreads();
+    double e0 = 0.0;
+    int failed = 0;
+    while (fabs(e - e0) > tol * e) {
+        e0 = e;
+        spmv_cta(A, x, sx);
+        a = 0.0;
+        for (int i = tid; i < n; i += 1024) a += sx[i] * sx[i];
+        const double nsx = sqrt(bsum(a));
+        if (nsx == 0.0) { failed = 1; break; }
+        spmv_cta(At, sx, x);
+        a = 0.0;
+        for (int i = tid; i < n; i += 1024) a += x[i] * x[i];
+        const double nx = sqrt(bsum(a));
+        e = nx / nsx;
+        const double inv = 1.0 / nx;
+        for (int i = tid; i < n; i += 1024) x[i] *= inv;
+        __syncthreads();
+        cnt += 1.0;
+        if (cnt > 100.0) break;
+    }
+    if (tid == 0) { out[0] = e; out[1] = cnt; out[2] = (double)failed; }
+}
+
+__global__ void colabs_rowsum_kernel(CsrDevView At, double* __restrict__ x) {
+    const int g = (blockIdx.x * 256 + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+    if (g >= At.n) return;
+    double s = 0.0;
+    for (int p = At.row_ptr[g] + sub; p < At.row_ptr[g + 1]; p += 8) s += fabs(At.val ? At.val[p] : At.uval);
+    const unsigned m = __activemask();
+    s += __shfl_xor_sync(m, s, 1);
+    s += __shfl_xor_sync(m, s, 2);
+    s += __shfl_xor_sync(m, s, 4);
+    if (sub == 0) x[At.row_order[g]] = s;
+}
+__global__ void vec_scale_kernel(double* __restrict__ x, int64_t n, double f) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= f;
+}
+
 // MATLAB normest(S, tol): power iteration on S'S from the column abs-sums
 inline void normest_dev(kr_ctx* ctx, const kr_matrix* M, double tol, double* est, int64_t* count) {
-    const CsrHost& H = M->host;
-    const int64_t n = H.n;
-    std::vector<double> x(n, 0.0);
-    for (int64_t i = 0; i < n; ++i)
-        for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) x[H.col[p]] += std::abs(H.val[p]);
-    double e = 0;
-    for (double v : x) e += v * v;
-    e = std::sqrt(e);
+    const int64_t n = M->dev.n;
+    if (n == 0) { *est = 0; *count = 0; return; }
+    DevBuf<double> x(ctx, n), sx(ctx, n), part(ctx, VEC_RED_CTAS), sc(ctx, 4);
+    static const int64_t small_nnz = [] { const char* e = getenv("KR_NORMEST_SMALL_NNZ"); return e ? atoll(e) : (int64_t)400000; }();
+    if (M->dev.nnz <= small_nnz) {
+        KR_LAUNCH(ctx, normest_small_kernel, 1, 1024, 0, M->dev.view(), M->T().view(), tol, x.p, sx.p, sc.p);
+        double h[3];
+        sc.download(h, 3);
+        if (h[2] != 0.0) fail(KR_ERR_UNSUPPORTED, "normest: S*x vanished");
+        *est = h[0];
+        *count = (int64_t)h[1];
+        return;
+    }
+    KR_LAUNCH(ctx, colabs_rowsum_kernel, (int)ceil_div(n * 8, 256), 256, 0, M->T().view(), x.p);
+    double h = 0;
+    vec_reduce<0>(ctx, x.p, x.p, n, part.p, sc.p);
+    sc.download(&h, 1);
+    double e = std::sqrt(h);
     int64_t cnt = 0;
     if (e == 0) { *est = 0; *count = 0; return; }
-    for (auto& v : x) v /= e;
-    CmMat dx(ctx, n, 1), dSx(ctx, n, 1), dy(ctx, n, 1);
-    upload_host_cm(ctx, x.data(), n, dx);
+    const int eg = ew_grid(ctx, n);
+    KR_LAUNCH(ctx, vec_scale_kernel, eg, 256, 0, x.p, n, 1.0 / e);
     double e0 = 0;
     while (std::abs(e - e0) > tol * e) {
         e0 = e;
-        spmm_cm(ctx, M, dx.p(), 1, dSx.p());                         // Sx = S*x
-        double nSx = 0, nx = 0;
-        KR_CUBLAS(cublasDnrm2(ctx->cublas, (int)n, dSx.p(), 1, &nSx));
-        if (nSx == 0) fail(KR_ERR_UNSUPPORTED, "normest: S*x vanished");
-        // x = S'*Sx
-        {
-            PanelBuf xb(ctx, n, 1), yb(ctx, n, 1);
-            cm_to_panel(ctx, dSx.p(), n, xb);
-            EpiPlain epi{yb.p(), xb.p(), 1.0, 0.0};
-            launch_spmm(ctx, M->T(), xb.p(), 1, epi, nullptr, 1);
-            panel_to_cm(ctx, yb, dy.p(), n);
-        }
-        KR_CUBLAS(cublasDnrm2(ctx->cublas, (int)n, dy.p(), 1, &nx));
-        e = nx / nSx;
-        const double inv = 1.0 / nx;
-        KR_CUDA(cudaMemcpyAsync(dx.p(), dy.p(), (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        KR_CUBLAS(cublasDscal(ctx->cublas, (int)n, &inv, dx.p(), 1));
+        spmv(ctx, M->dev, x.p, sx.p);                                // Sx = S*x
+        vec_reduce<0>(ctx, sx.p, sx.p, n, part.p, sc.p);
+        spmv(ctx, M->T(), sx.p, x.p);                                // x = S'*Sx
+        vec_reduce<0>(ctx, x.p, x.p, n, part.p, sc.p + 1);
+        double hh[2];
+        sc.download(hh, 2);                                          // one synchronisation per iteration
+        if (hh[0] == 0) fail(KR_ERR_UNSUPPORTED, "normest: S*x vanished");
+        const double nx = std::sqrt(hh[1]);
+        e = nx / std::sqrt(hh[0]);
+        KR_LAUNCH(ctx, vec_scale_kernel, eg, 256, 0, x.p, n, 1.0 / nx);
         cnt += 1;
         if (cnt > 100) break;
     }

@@ -3,8 +3,6 @@
 // negative kr_status with a thread-local message.
 #pragma once
 #include <cuda_runtime.h>
-#include <cublas_v2.h>
-#include <cusolverDn.h>
 
 #include <cstdarg>
 #include <cstdint>
@@ -47,19 +45,6 @@ struct Error : std::runtime_error {
             ::kr::fail(KR_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, \
                        __LINE__, cudaGetErrorString(e_));                                       \
     } while (0)
-#define KR_CUBLAS(call)                                                                         \
-    do {                                                                                        \
-        cublasStatus_t s_ = (call);                                                             \
-        if (s_ != CUBLAS_STATUS_SUCCESS)                                                        \
-            ::kr::fail(KR_ERR_CUDA, "cuBLAS error %d at %s:%d", (int)s_, __FILE__, __LINE__);   \
-    } while (0)
-#define KR_CUSOLVER(call)                                                                       \
-    do {                                                                                        \
-        cusolverStatus_t s_ = (call);                                                           \
-        if (s_ != CUSOLVER_STATUS_SUCCESS)                                                      \
-            ::kr::fail(KR_ERR_CUDA, "cuSOLVER error %d at %s:%d", (int)s_, __FILE__, __LINE__); \
-    } while (0)
-
 // wraps an extern "C" body: exceptions -> status + message
 template <class F>
 int guarded(F&& f) {
@@ -87,8 +72,6 @@ struct kr_ctx {
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host<->device staging that overlaps compute (created on first use)
-    cublasHandle_t cublas = nullptr;
-    cusolverDnHandle_t cusolver = nullptr;
     // counters: launches, spmm launches, matvecs, h2d bytes, d2h bytes
     int64_t counters[5] = {0, 0, 0, 0, 0};
     // optional SpMM timing

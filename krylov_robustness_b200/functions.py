@@ -164,9 +164,10 @@ def trace_fun_update(A, U, B, tol=1e-12, it=None, debug=0, fun="exp"):
     return x.value, k.value, bool(lucky.value)
 
 
-def trace_fun_update_edges(A, E, b_offdiag, tol=1e-12, it=None, fun="exp"):
+def trace_fun_update_edges(A, E, b_offdiag, tol=1e-12, it=None, fun="exp", b_self=None):
     """All candidates of the loop at functions/krylov_miobi.m:76-99 in one call: for each row (i, j) of
-    E (1-based) U = [e_i e_j], B = b_offdiag*[0 1;1 0] (B = b_offdiag when i == j).
+    E (1-based) U = [e_i e_j], B = b_offdiag*[0 1;1 0]; a self loop i == j is the rank-one update B = b_self
+    (default b_offdiag; the reference does not rescale it, krylov_miobi.m:88-94).
     Returns (Xm, iter, lucky) arrays."""
     M = _mat(A)
     it = _default_it(M, it)
@@ -175,8 +176,9 @@ def trace_fun_update_edges(A, E, b_offdiag, tol=1e-12, it=None, fun="exp"):
     x = np.zeros(nE)
     k = np.zeros(nE, dtype=np.int64)
     lucky = np.zeros(nE, dtype=np.int32)
-    check(M.ctx.lib.kr_trace_fun_update_edges(M.ctx.h, M.h, nE, _ptr(E), float(b_offdiag), float(tol), it, fun_id(fun),
-                                              _ptr(x), _ptr(k), _ptr(lucky)))
+    check(M.ctx.lib.kr_trace_fun_update_edges_ex(M.ctx.h, M.h, nE, _ptr(E), float(b_offdiag),
+                                                 float(b_offdiag if b_self is None else b_self), float(tol), it,
+                                                 fun_id(fun), _ptr(x), _ptr(k), _ptr(lucky)))
     return x, k, lucky.astype(bool)
 
 
@@ -504,7 +506,7 @@ def krylov_miobi(A, k, E=None, tol=1e-12, it=None, poles=np.inf, debug=0, miobi=
         if scorer is not None:
             vals = np.asarray(scorer(M, E, sign / rescale, tol, it))
         else:
-            vals = trace_fun_update_edges(M, E, sign / rescale, tol, it, "exp")[0]
+            vals = trace_fun_update_edges(M, E, sign / rescale, tol, it, "exp", b_self=sign)[0]
         best, bestval = select_candidate(vals, miobi)
         chosen = E[best].copy()
         E = np.delete(E, best, axis=0)
@@ -550,7 +552,7 @@ def greedy_krylov(A, k, Q=0, centrality=None, order="mult", tol=1e-12, it=None, 
         if scorer is not None:
             vals = np.asarray(scorer(M, E, sign / rescale, tol, it))
         else:
-            vals = trace_fun_update_edges(M, E, sign / rescale, tol, it, "exp")[0]
+            vals = trace_fun_update_edges(M, E, sign / rescale, tol, it, "exp", b_self=sign)[0]
         best, bestval = select_candidate(vals, miobi)
         chosen = E[best].copy()
         M.set_edges([chosen[0]], [chosen[1]], newval)

@@ -16,7 +16,7 @@ end
 sgn = 1; if strcmp(miobi, 'break'), sgn = -1; end
 rob = 0; edges = zeros(0, 2);
 for j = 1:min(k, size(E, 1))
-    vals = kr_mex('trace_fun_update_edges', A, double(E), sgn/rescale, tol, it, 'exp');
+    vals = kr_mex('trace_fun_update_edges', A, double(E), sgn/rescale, tol, it, 'exp', sgn);   % self loops are not rescaled (:88-94)
     if strcmp(miobi, 'break'), mx = [0 inf]; else, mx = [0 -inf]; end
     for h = 1:size(E, 1)
         if (sgn < 0 && vals(h) < mx(2)) || (sgn > 0 && vals(h) > mx(2)), mx = [h vals(h)]; end

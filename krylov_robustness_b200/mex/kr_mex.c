@@ -13,8 +13,10 @@
  * Sparse A arrives as MATLAB CSC (Jc, Ir, Pr).  Every A on this path is symmetric
  * (functions/greedy_krylov.m:27, functions/krylov_miobi.m:26, functions/fun_and_grad_krylov_fun.m:22),
  * so its CSC arrays are its CSR arrays and are passed through unchanged; an unsymmetric A is
- * transposed by the wrapper (A.') before the call.  Device copies of A are cached per mxArray data
- * pointer + nnz and released by mexAtExit.
+ * transposed by the wrapper (A.') before the call.  Device copies of A are cached, keyed on (n, nnz, a 64-bit
+ * fingerprint of the CONTENT of Jc / Ir / Pr): MATLAB re-uses freed addresses, so the data pointer identifies
+ * nothing (a fresh `A + XX + XX'` of the Hessian callbacks lands on the old address with the same pattern and
+ * nnz).  Krylov state handles are tracked here too; both are released by mexAtExit.
  */
 #include <string.h>
 #include <stdlib.h>
@@ -23,13 +25,50 @@
 
 static kr_ctx* g_ctx = NULL;
 #define KR_CACHE 8
-static struct { const void* key; mwSize nnz; kr_matrix* M; } g_cache[KR_CACHE];
+static struct { uint64_t key; mwSize n, nnz; kr_matrix* M; } g_cache[KR_CACHE];
 static int g_next = 0;
+#define KR_MAX_KRYLOV 4096
+static kr_krylov* g_krylov[KR_MAX_KRYLOV];      /* live Krylov handles (freed by 'krylov_free' or at exit) */
 
 static void at_exit(void) {
     int i;
+    for (i = 0; i < KR_MAX_KRYLOV; ++i) if (g_krylov[i]) { kr_krylov_destroy(g_krylov[i]); g_krylov[i] = NULL; }
     for (i = 0; i < KR_CACHE; ++i) if (g_cache[i].M) { kr_matrix_destroy(g_cache[i].M); g_cache[i].M = NULL; }
     if (g_ctx) { kr_ctx_destroy(g_ctx); g_ctx = NULL; }
+}
+
+static void track_krylov(kr_krylov* st) {
+    int i;
+    for (i = 0; i < KR_MAX_KRYLOV; ++i) if (!g_krylov[i]) { g_krylov[i] = st; return; }
+    kr_krylov_destroy(st);
+    mexErrMsgTxt("krylov_b200: too many live Krylov handles (clear the params structs that are no longer needed)");
+}
+static int untrack_krylov(kr_krylov* st) {      /* 1 if the handle was live */
+    int i;
+    for (i = 0; i < KR_MAX_KRYLOV; ++i) if (g_krylov[i] == st) { g_krylov[i] = NULL; return 1; }
+    return 0;
+}
+static kr_krylov* live_krylov(const mxArray* h) {
+    kr_krylov* st = *(kr_krylov**)mxGetData(h);
+    int i;
+    for (i = 0; i < KR_MAX_KRYLOV; ++i) if (st && g_krylov[i] == st) return st;
+    mexErrMsgTxt("krylov_b200: stale or foreign Krylov handle");
+    return NULL;
+}
+
+/* 64-bit content fingerprint (four interleaved multiply-xor lanes over 8-byte words) */
+static uint64_t mix64(uint64_t h, uint64_t x) {
+    h ^= x;
+    h *= 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+static uint64_t hash_words(uint64_t seed, const void* data, size_t bytes) {
+    const uint64_t* w = (const uint64_t*)data;
+    size_t k = bytes / 8, i = 0;
+    uint64_t h0 = seed, h1 = seed ^ 0xA0761D6478BD642Full, h2 = seed ^ 0xE7037ED1A0B428DBull, h3 = seed ^ 0x8EBC6AF09C88C6E3ull;
+    for (; i + 4 <= k; i += 4) { h0 = mix64(h0, w[i]); h1 = mix64(h1, w[i + 1]); h2 = mix64(h2, w[i + 2]); h3 = mix64(h3, w[i + 3]); }
+    for (; i < k; ++i) h0 = mix64(h0, w[i]);
+    return mix64(mix64(mix64(h0, h1), h2), h3);
 }
 
 static void chk(int status) {
@@ -47,11 +86,15 @@ static kr_matrix* matrix_of(const mxArray* A) {
     const mwIndex *jc, *ir;
     int64_t *rp, *ci;
     kr_matrix* M = NULL;
+    uint64_t key;
     if (!mxIsSparse(A) || !mxIsDouble(A)) mexErrMsgTxt("A must be a real sparse double matrix");
     if (mxGetM(A) != mxGetN(A)) mexErrMsgTxt("The matrix A should be square");
     n = mxGetN(A); jc = mxGetJc(A); ir = mxGetIr(A); nnz = jc[n];
+    key = hash_words(0x243F6A8885A308D3ull ^ (uint64_t)n, jc, (n + 1) * sizeof(mwIndex));
+    key = hash_words(key, ir, nnz * sizeof(mwIndex));
+    key = hash_words(key, mxGetPr(A), nnz * sizeof(double));
     for (i = 0; i < KR_CACHE; ++i)
-        if (g_cache[i].M && g_cache[i].key == (const void*)mxGetPr(A) && g_cache[i].nnz == nnz) return g_cache[i].M;
+        if (g_cache[i].M && g_cache[i].key == key && g_cache[i].n == n && g_cache[i].nnz == nnz) return g_cache[i].M;
     rp = (int64_t*)mxMalloc((n + 1) * sizeof(int64_t));
     ci = (int64_t*)mxMalloc((nnz ? nnz : 1) * sizeof(int64_t));
     for (i = 0; i <= (int)n; ++i) rp[i] = (int64_t)jc[i];
@@ -59,7 +102,7 @@ static kr_matrix* matrix_of(const mxArray* A) {
     chk(kr_matrix_create(ctx(), (int64_t)n, (int64_t)nnz, rp, ci, mxGetPr(A), &M));
     mxFree(rp); mxFree(ci);
     if (g_cache[g_next].M) kr_matrix_destroy(g_cache[g_next].M);
-    g_cache[g_next].key = (const void*)mxGetPr(A); g_cache[g_next].nnz = nnz; g_cache[g_next].M = M;
+    g_cache[g_next].key = key; g_cache[g_next].n = n; g_cache[g_next].nnz = nnz; g_cache[g_next].M = M;
     g_next = (g_next + 1) % KR_CACHE;
     return M;
 }
@@ -104,15 +147,16 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = scalar(x);
         if (nlhs > 1) plhs[1] = scalar((double)it);
         if (nlhs > 2) plhs[2] = mxCreateLogicalScalar(lucky != 0);
-    } else if (!strcmp(op, "trace_fun_update_edges")) {            /* [Xm,iter,lucky] = (A,E,b,tol,it,fun) */
+    } else if (!strcmp(op, "trace_fun_update_edges")) {            /* [Xm,iter,lucky] = (A,E,b,tol,it,fun[,b_self]) */
         kr_matrix* M = matrix_of(prhs[0]);
         mwSize nE = mxGetM(prhs[1]), i;
         int64_t* E = to_i64(prhs[1], NULL);
         int64_t* it = (int64_t*)mxMalloc((nE ? nE : 1) * sizeof(int64_t));
         int* lk = (int*)mxMalloc((nE ? nE : 1) * sizeof(int));
         plhs[0] = mxCreateDoubleMatrix(nE, 1, mxREAL);
-        chk(kr_trace_fun_update_edges(ctx(), M, (int64_t)nE, E, mxGetScalar(prhs[2]), mxGetScalar(prhs[3]),
-                                      (int64_t)mxGetScalar(prhs[4]), fun_of(prhs[5]), mxGetPr(plhs[0]), it, lk));
+        chk(kr_trace_fun_update_edges_ex(ctx(), M, (int64_t)nE, E, mxGetScalar(prhs[2]),
+                                         nrhs > 6 ? mxGetScalar(prhs[6]) : mxGetScalar(prhs[2]), mxGetScalar(prhs[3]),
+                                         (int64_t)mxGetScalar(prhs[4]), fun_of(prhs[5]), mxGetPr(plhs[0]), it, lk));
         if (nlhs > 1) { plhs[1] = mxCreateDoubleMatrix(nE, 1, mxREAL); for (i = 0; i < nE; ++i) mxGetPr(plhs[1])[i] = (double)it[i]; }
         if (nlhs > 2) { plhs[2] = mxCreateDoubleMatrix(nE, 1, mxREAL); for (i = 0; i < nE; ++i) mxGetPr(plhs[2])[i] = (double)lk[i]; }
         mxFree(E); mxFree(it); mxFree(lk);
@@ -205,12 +249,17 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         /* state handle travels as a uint64 scalar inside params.handle:
          * [V,H,K,last,lucky,handle] = kr_mex('krylov_start', A, b, arnoldi) / ('krylov_extend', handle) */
         kr_krylov* st = NULL; int lucky = 0; int64_t d[5];
-        if (!strcmp(op, "krylov_free")) { kr_krylov_destroy(*(kr_krylov**)mxGetData(prhs[0])); return; }
+        if (!strcmp(op, "krylov_free")) {       /* idempotent: onCleanup of a copied params struct may fire twice */
+            kr_krylov* dead = *(kr_krylov**)mxGetData(prhs[0]);
+            if (untrack_krylov(dead)) kr_krylov_destroy(dead);
+            return;
+        }
         if (!strcmp(op, "krylov_start")) {
             chk(kr_krylov_start(ctx(), matrix_of(prhs[0]), (int)mxGetScalar(prhs[2]), (int64_t)mxGetN(prhs[1]),
                                 mxGetPr(prhs[1]), (int64_t)mxGetM(prhs[1]), &st, &lucky));
+            track_krylov(st);
         } else {
-            st = *(kr_krylov**)mxGetData(prhs[0]);
+            st = live_krylov(prhs[0]);
             chk(kr_krylov_extend(st, &lucky));
         }
         chk(kr_krylov_dims(st, d));
