@@ -106,30 +106,46 @@ def cpu_slq_rate(A, cols_per_proc, procs, m):
     return procs * cols_per_proc * m / dt, dt
 
 
+def cpu_block_sweep(A, m):
+    """Pick the per-process probe-block width for the CPU arm: SciPy's CSR x dense product re-reads A once per
+    block, so a 2-column block (round 1) starves it.  One core, 8 Lanczos steps, widths 8 / 16 / 32."""
+    best = (0.0, 16)
+    for cols in (16, 32):
+        rate, _ = cpu_slq_rate(A, cols, 1, min(m, 4))
+        best = max(best, (rate, cols))
+    return best[1]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import shutil
+    interp = [x for x in ("octave", "octave-cli", "matlab") if shutil.which(x)]
     A, _ = build_graph()
     cores = os.cpu_count() or 1
-    cols = 2
+    cols = int(os.environ.get("KR_BENCH_CPU_COLS", 0)) or cpu_block_sweep(A, M_STEPS)
+    # bounded sample per step: every process runs `cols` probes for m_cpu Lanczos steps (the per-matvec cost of the
+    # recurrence does not depend on the step count), ~8 s per step on 16 cores
+    m_cpu = int(os.environ.get("KR_BENCH_CPU_M", 4))
     times = []
     for it in range(args.warmup + args.steps):
-        rate, dt = cpu_slq_rate(A, cols, cores, M_STEPS)
+        rate, dt = cpu_slq_rate(A, cols, cores, m_cpu)
         if it >= args.warmup:
             times.append((rate, dt))
     rate = float(np.mean([r for r, _ in times]))
     ms = float(np.mean([d for _, d in times]) * 1e3)
-    sample = "%d probes (%d per process x %d processes) x %d Lanczos steps of the same graph per step" % (
-        cols * cores, cols, cores, M_STEPS)
+    sample = "%d probes (%d per process x %d processes, block width picked by a one-core sweep over 16/32) x %d Lanczos " \
+             "steps of the same graph per step" % (cols * cores, cols, cores, m_cpu)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(max(int(args.gpus), 1)),      # the arm's config at this N (the CPU rate does not scale with N)
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference is MATLAB-only (no MATLAB/Octave in the image): this is the NumPy/SciPy "
-                    "oracle port of functions/*.m on the host cores"}
+            "interpreters_found": interp,
+            "note": "reference is MATLAB-only; probed for octave / octave-cli / matlab on PATH: %s. This is the NumPy/SciPy "
+                    "oracle port of functions/*.m on the host cores" % (interp or "none")}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -188,6 +204,66 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- our arm
+PEAK_SOURCE = ["fallback"]
+
+
+def peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            v = float(json.load(f)["hbm_gbs"])
+        PEAK_SOURCE[0] = "measured"
+        return v
+    except Exception:
+        PEAK_SOURCE[0] = "fallback"
+        return 6650.0
+
+
+def bench_c4(kr, ctx):
+    """expmv (Al-Mohy-Higham) on the C4 graph: ms per fused Taylor term and its fraction of the HBM roofline
+    (algorithmic bytes 4*nnz [pattern-only CSR] + 4*(n+1) + 32*n*q: read b, write b', read-modify-write f)."""
+    from krylov_robustness_b200.graphs import rmat_graph_device
+    scale = int(os.environ.get("KR_BENCH_C4_SCALE", 24))
+    nnz_t = int(os.environ.get("KR_BENCH_C4_NNZ", 1 << (scale + 4)))
+    q = int(os.environ.get("KR_BENCH_C4_Q", 64))
+    t0 = time.perf_counter()
+    indptr, indices = rmat_graph_device(scale, nnz_t, seed=2, device=ctx.device)
+    n, nnz = indptr.size - 1, indices.size
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    M4 = kr.Matrix.from_csr_arrays(n, indptr, indices, 1.0, ctx)
+    del indptr, indices
+    upload_s = time.perf_counter() - t0
+    lam4 = float(kr.normest(M4, 1e-3)[0])                 # symmetric: ||A||_2 (device power iteration)
+    tscale = 8.0 / lam4                                   # ||tA||_2 ~ 8: s*m = O(10^2), e^{t lambda} finite
+    b = np.random.default_rng(3).standard_normal((n, q))
+    kr.expmv(tscale, M4, b[:, :8])                        # warm-up
+    ctx.set_timing(True)
+    ctx.spmm_time(reset=True)
+    c0 = ctx.counters()
+    t0 = time.perf_counter()
+    f, s, mdeg, mv, mvd, unA = kr.expmv(tscale, M4, b)
+    wall = time.perf_counter() - t0
+    ms, launches = ctx.spmm_time(reset=True)
+    c1 = ctx.counters()
+    ctx.set_timing(False)
+    terms = mv - mvd
+    # the timed SpMM launches are the Taylor terms (q columns each); the 1-norm power sequence runs on the SpMV kernel
+    ms_term = ms / max(launches, 1)
+    bytes_term = 4.0 * nnz + 4.0 * (n + 1) + 32.0 * n * q
+    peak = peak_gbs()
+    out = {"metric": "expmv_taylor_term", "workload": "C4: R-MAT scale %d, %d stored entries, %d right-hand sides, ||tA||_2 ~ 8, "
+                                                      "normAm / degree selection on the device" % (scale, nnz, q),
+           "n": n, "nnz": nnz, "q": q, "s": int(s), "m": int(mdeg), "mv": int(mv), "mvd": int(mvd), "unA": int(unA),
+           "taylor_terms_timed": int(launches), "ms_per_taylor_term": ms_term,
+           "matvecs_per_sec": launches * q / (ms * 1e-3) if ms > 0 else None,
+           "algorithmic_bytes_per_term": bytes_term, "achieved_GBs": bytes_term / (ms_term * 1e-3) / 1e9,
+           "peak_GBs": peak, "frac": bytes_term / (ms_term * 1e-3) / 1e9 / peak,
+           "expmv_call_wall_s_incl_h2d_d2h": wall, "graph_gen_s": gen_s, "matrix_analysis_upload_s": upload_s,
+           "gpu_launches": c1["launches"] - c0["launches"], "lambda_max_est": lam4}
+    del M4, f, b
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -205,10 +281,12 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    from krylov_robustness_b200 import parallel as P
     A, lam = build_graph()
     n, nnz = A.shape[0], A.nnz
     ctx = kr.Context(local)
     M = kr.Matrix(A, ctx)
+    pattern_only = M.info()["pattern_only"]
     k, m = K_PROBES, M_STEPS
     Zdev = kr.Dense(n, k, ctx).fill_rademacher(PROBE_SEED, col_offset=rank * k)
     # pinned host copy of the same probes for the end-to-end arm (column-major n x k)
@@ -280,37 +358,66 @@ def run_ours(args):
     ctx.set_timing(False)
     tr_value = float(tr_dev.item())
 
-    # ---- secondary metric of BASELINE.json: candidate edges scored per second (config C5 shape, bounded):
-    # missing edges among the highest-degree nodes of the same graph, 1024 candidates per GPU, scored by
-    # the batched trace_fun_update path (rank-2 block Lanczos per candidate), one all-gather per round.
+    # ---- strong scaling of the headline (the 512 probe columns SPLIT across the ranks)
+    strong = None
+    if world > 1 and os.environ.get("KR_BENCH_STRONG", "1") != "0":
+        lo, hi = P.shard_bounds(k)
+        Zs = kr.Dense(n, hi - lo, ctx).fill_rademacher(PROBE_SEED, col_offset=lo)
+
+        def step_strong():
+            s_local = kr.slq_trace(M, Zs, m, "exp") * (hi - lo)
+            acc.fill_(s_local / k)
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            return acc
+        step_strong()
+        ms_s, tr_s = timed(step_strong, args.steps)
+        strong = {"value": k * m * args.steps / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / args.steps,
+                  "probes_total": k, "probes_per_gpu": hi - lo, "trace_estimate": float(tr_s.item()),
+                  "note": "same 512 probes split across the ranks (strong scaling); the headline `value` is weak scaling"}
+        del Zs
+
+    # ---- secondary metric of BASELINE.json (config C5): candidate edges scored per second.  10^5 missing-edge
+    # candidates from find_top_missing_edges(A, leading-eigenvector centrality, 1e5, 'min') on the same graph, SPLIT
+    # across the ranks (12 500 per GPU at 8), scored by the batched rank-2 trace_fun_update path, one all-gather of
+    # the scores + the reference's first-wins arg-max per round.
     secondary = None
     if os.environ.get("KR_BENCH_EDGES", "1") != "0":
-        from krylov_robustness_b200 import parallel as P
-        ncand = int(os.environ.get("KR_BENCH_NCAND", 1024)) * world
-        deg = np.diff(A.indptr)
-        top = np.argsort(-deg, kind="stable")[:max(64, int(2.2 * np.sqrt(2 * ncand)))]
-        sub = A[top][:, top].toarray()
-        ii, jj = np.where(np.triu(sub == 0, 1))
-        E = np.stack([top[jj] + 1, top[ii] + 1], 1)[:ncand].astype(np.int64)
+        ncand = int(os.environ.get("KR_BENCH_C5_CAND", 100_000))
+        t0 = time.perf_counter()
+        cvec = kr.compute_centrality(M, "eig", 1e-10)
+        E = kr.find_top_missing_edges(A, cvec, ncand, "min")
+        t_cand = time.perf_counter() - t0
         tol_e = 1e-6 * float(np.exp(1.0))                 # 1e-6 * exp(||A||), A scaled to spectral radius ~1
         b_off = 1.0 / lam                                 # an edge of the unscaled graph, in the scaled units
 
-        def score_round():
+        def score_round(Ecand):
             its = []
 
             def local(Es):
                 x, it, _ = kr.trace_fun_update_edges(M, Es, b_off, tol_e, 100, "exp")
                 its.append(it)
                 return x
-            vals = P.sharded_edge_scores(local, E)
+            vals = P.sharded_edge_scores(local, Ecand)
             return vals, (np.concatenate(its) if its else np.zeros(0))
-        score_round()                                     # warm-up (allocations, attribute setup)
-        ms_edges, (vals, its) = timed(score_round, 1)
+        score_round(E[:64 * world])                       # warm-up (allocations, attribute setup)
+        ms_edges, (vals, its) = timed(lambda: score_round(E), 1)
+        lo, hi = P.shard_bounds(E.shape[0])
+        # edge roofline of SURVEY.md 8(d): matvec roofline / (2 * mean steps)
+        b_mv = ((4.0 if pattern_only else 12.0) * nnz + 4.0 * (n + 1)) / 512 + 16.0 * n
         secondary = {"metric": "edges_scored_per_sec", "value": E.shape[0] / (ms_edges * 1e-3), "unit": "edge/s",
-                     "candidates": int(E.shape[0]), "ms_per_round": ms_edges,
+                     "workload": "C5: %d candidates of find_top_missing_edges(A, eig centrality, 'min') on the C3 graph, "
+                                 "split across %d rank(s)" % (E.shape[0], world),
+                     "candidates": int(E.shape[0]), "candidates_this_gpu": int(hi - lo), "ms_per_round": ms_edges,
+                     "distinct_nodes": int(np.unique(E).size),
                      "mean_block_lanczos_steps": float(its.mean()) if its.size else None,
+                     "steps_histogram_rank0": {int(a): int(b) for a, b in zip(*np.unique(its, return_counts=True))},
+                     "candidate_generation_s": t_cand,
                      "best_candidate": [int(v) for v in E[int(np.argmax(vals))]],
+                     "scaling": "strong",
                      "note": "one greedy 'make' round: all candidates scored + all-gather + first-wins arg-max"}
+        if its.size:
+            secondary["roofline_edges_per_sec_per_gpu"] = peak_gbs() * 1e9 / b_mv / (2.0 * float(its.mean()))
+            secondary["frac_of_edge_roofline"] = secondary["value"] / world / secondary["roofline_edges_per_sec_per_gpu"]
 
     for _ in range(1):
         step_e2e()
@@ -323,20 +430,20 @@ def run_ours(args):
     ms_e2e8, tr_e2e8 = timed(step_e2e_sign, e2e_steps)
     g1 = ctx.counters()
 
+    # ---- config C4: expmv Taylor path on R-MAT 2^24 nodes / 2^28 stored entries, 64 right-hand sides, normAm on the
+    # device.  One GPU's worth of work (A replicated, columns would be split): measured on rank 0 when N == 1.
+    secondary_c4 = None
+    if rank == 0 and os.environ.get("KR_BENCH_C4", "1" if world == 1 else "0") != "0":
+        secondary_c4 = bench_c4(kr, ctx)
+
     if rank == 0:
         mv_step = k * m * world
         value = mv_step * args.steps / (ms_dev * 1e-3)
         e2e = mv_step * e2e_steps / (ms_e2e * 1e-3)
-        peaks = {}
-        src = "fallback"
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-            src = "measured"
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        b_spmm = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n * k
+        peak = peak_gbs()
+        src = PEAK_SOURCE[0]
+        # algorithmic bytes with the matrix as it is actually stored (pattern-only CSR: 4 B per nonzero)
+        b_spmm = (4.0 if pattern_only else 12.0) * nnz + 4.0 * (n + 1) + 16.0 * n * k
         per_launch_ms = spmm_ms / max(spmm_launches, 1)
         achieved = b_spmm / (per_launch_ms * 1e-3) / 1e9
         traffic = None
@@ -377,7 +484,7 @@ def run_ours(args):
                                     "achieved_tb_per_s": 8.0 * nnz * k / (per_launch_ms * 1e-3) / 1e12,
                                     "microbench_ceiling_tb_per_s": 14.8,
                                     "source": "profiles/r01_l2_gather_microbench.json"}},
-            "secondary": secondary,
+            "secondary": secondary, "secondary_c4": secondary_c4, "strong_scaling": strong,
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": "oracle.slq_trace (NumPy/SciPy port of the reference path) on 4 probes x %d steps "
                                        "of the same graph, %.1f s" % (m, cpu_dt)},

@@ -140,6 +140,13 @@ int  kr_frechet_hessian(kr_ctx* ctx, const kr_matrix* Atilde, int64_t nomega, co
 /* MATLAB normest(A,tol) as used at functions/fun_and_grad_krylov_fun.m:27 */
 int  kr_normest(kr_ctx* ctx, const kr_matrix* A, double tol, double* est, int64_t* count);
 
+/* c = compute_centrality(A, type)                   functions/compute_centrality.m:15-17 ('eig'), :20-26 ('pr')
+ * kind 0: |leading eigenvector| of A (the reference calls eigs(A,1)); kind 1: PageRank vector, alpha = 0.85.
+ * Power iteration on the device (one launch for the reference's graph sizes), unit 2-norm, stop when the
+ * iterate moves by less than tol. */
+int  kr_compute_centrality(kr_ctx* ctx, const kr_matrix* A, int kind, double tol, int64_t maxit, double* c,
+                           int64_t* iters, int* converged);
+
 /* ------------------------------------------------------------------ expmv family */
 /* [c,mv] = normAm(A,m)                               functions/normAm.m:1-52
  * scale: the estimate is of ||(scale*A)^m||_1 (expmv passes t*A, functions/expmv.m:41). */

@@ -57,6 +57,7 @@ PROTOTYPES = {
                                c_dp, VP],
     "kr_frechet_hessian": [VP, VP, c_i64, VP, C.c_int, C.c_double, c_i64, VP, c_ip],
     "kr_normest": [VP, VP, C.c_double, c_dp, c_ip],
+    "kr_compute_centrality": [VP, VP, C.c_int, C.c_double, c_i64, VP, c_ip, c_intp],
     "kr_normAm": [VP, VP, C.c_double, c_i64, c_dp, c_ip],
     "kr_select_taylor_degree": [VP, VP, C.c_double, c_i64, c_i64, c_i64, C.c_int, C.c_int,
                                 VP, c_ip, VP, c_intp],

@@ -167,53 +167,22 @@ int kr_matrix_set_edges(kr_matrix* A, int64_t count, const int64_t* ii, const in
     return guarded([&] {
         if (!A) fail(KR_ERR_ARG, "null matrix");
         KR_CUDA(cudaSetDevice(A->ctx->device));
-        CsrHost& H = A->host;
+        const CsrHost& H = A->host;
         const int64_t n = H.n;
-        // gather edits per row (both triangles), then rebuild the touched rows
-        std::map<int64_t, std::map<int32_t, double>> edits;
         for (int64_t e = 0; e < count; ++e) {
-            int64_t i = ii[e] - 1, j = jj[e] - 1;
+            const int64_t i = ii[e] - 1, j = jj[e] - 1;
             if (i < 0 || i >= n || j < 0 || j >= n) fail(KR_ERR_ARG, "kr_matrix_set_edges: index out of range");
-            edits[i][(int32_t)j] = v[e];
-            edits[j][(int32_t)i] = v[e];
+            // both triangles (functions/krylov_miobi.m:129-135); recorded as (new value - stored value)
+            A->pending[{i, j}] = v[e] - host_entry(H, i, j);
+            A->pending[{j, i}] = v[e] - host_entry(H, j, i);
         }
-        // rebuild only the touched rows, then copy the untouched ones in parallel into their new places
-        std::map<int64_t, std::vector<std::pair<int32_t, double>>> rebuilt;
-        for (auto& ed : edits) {
-            const int64_t i = ed.first;
-            std::map<int32_t, double> row;
-            for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) row[H.col[p]] = H.val[p];
-            for (auto& kv : ed.second) row[kv.first] = kv.second;
-            auto& out = rebuilt[i];
-            for (auto& kv : row)
-                if (kv.second != 0.0) out.emplace_back(kv.first, kv.second);   // MATLAB sparse assignment of 0 removes the entry
-        }
-        CsrHost N;
-        N.n = n;
-        N.row_ptr.assign(n + 1, 0);
-        {
-            auto it = rebuilt.begin();
-            for (int64_t i = 0; i < n; ++i) {
-                int64_t len = H.row_ptr[i + 1] - H.row_ptr[i];
-                if (it != rebuilt.end() && it->first == i) { len = (int64_t)it->second.size(); ++it; }
-                N.row_ptr[i + 1] = N.row_ptr[i] + len;
-            }
-        }
-        N.col.resize((size_t)N.row_ptr[n]);
-        N.val.resize((size_t)N.row_ptr[n]);
-#pragma omp parallel for schedule(dynamic, 4096)
-        for (int64_t i = 0; i < n; ++i) {
-            auto it = rebuilt.find(i);
-            if (it == rebuilt.end()) {
-                std::copy(H.col.begin() + H.row_ptr[i], H.col.begin() + H.row_ptr[i + 1], N.col.begin() + N.row_ptr[i]);
-                std::copy(H.val.begin() + H.row_ptr[i], H.val.begin() + H.row_ptr[i + 1], N.val.begin() + N.row_ptr[i]);
-            } else {
-                int64_t w = N.row_ptr[i];
-                for (auto& kv : it->second) { N.col[(size_t)w] = kv.first; N.val[(size_t)w] = kv.second; ++w; }
-            }
-        }
-        H = std::move(N);
-        analyse_and_upload(A, /*keep_symmetric=*/true);
+        for (auto it = A->pending.begin(); it != A->pending.end();)
+            it = (it->second == 0.0) ? A->pending.erase(it) : std::next(it);
+        // The device keeps the stored CSR untouched and applies the few pending entries on the fly in the SpMM and
+        // in the candidate-seed kernel (the greedy loop's only consumers): no host rebuild, no re-upload of A per
+        // round.  Unsymmetric matrices (a transposed copy exists) and very long edit lists take the rebuild.
+        if (!A->symmetric || A->pending.size() > KR_MAX_PENDING || getenv("KR_SET_EDGES_REBUILD")) flush_pending(A);
+        else upload_pending(A);
     });
 }
 

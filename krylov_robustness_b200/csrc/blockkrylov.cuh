@@ -501,10 +501,15 @@ inline TfuResult trace_fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64
         if (SG.count < sz) { SG.reset(ctx, sz); F.reset(ctx, sz); }
         const double t1 = wide_prof().on ? WideProf::now() : 0.0;
         KR_LAUNCH(ctx, assemble_proj_kernel, ew_grid(ctx, (int64_t)nn * nn), 256, 0, st->hblocks(), nn, ws.CmS.p, (int)rk, SG.p);
-        symfun_batched(ctx, SG.p, nn, 2, fun, ws.norm_bound, F.p, ew);
-        KR_LAUNCH(ctx, trace_diff_kernel, 1, 256, 0, F.p, F.p + (size_t)nn * nn, nn, xm.p);
-        KR_CUDA(cudaMemcpyAsync(&out.Xm, xm.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        sync_lucky(st);                                       // the step's only synchronisation
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            ew.begin(ctx, attempt == 1);
+            symfun_batched(ctx, SG.p, nn, 2, fun, ws.norm_bound, F.p, ew);
+            KR_LAUNCH(ctx, trace_diff_kernel, 1, 256, 0, F.p, F.p + (size_t)nn * nn, nn, xm.p);
+            KR_CUDA(cudaMemcpyAsync(&out.Xm, xm.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            ew.enqueue_readback(ctx);
+            sync_lucky(st);                                   // the step's only synchronisation
+            if (ew.accept()) break;
+        }
         if (wide_prof().on) { wide_prof().fun += WideProf::now() - t1; wide_prof().n_fun++; wide_prof().max_dim = std::max(wide_prof().max_dim, nn); }
         out.lucky = st->lucky;
         bool done = false;
@@ -576,23 +581,28 @@ inline FuInfo fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64_t rk, co
         if (SG.count < 2 * sz) { SG.reset(ctx, 2 * sz); F.reset(ctx, 2 * sz); D.reset(ctx, sz); }
         const double t1 = wide_prof().on ? WideProf::now() : 0.0;
         KR_LAUNCH(ctx, assemble_proj_kernel, ew_grid(ctx, (int64_t)sz), 256, 0, st->hblocks(), nn, ws.CmS.p, (int)rk, SG.p);
-        symfun_batched(ctx, SG.p, nn, 2, fun, ws.norm_bound, F.p, ew);
         Xs.emplace_back(ctx, sz);
         Xdim.push_back(nn);
-        KR_LAUNCH(ctx, axpby_kernel, ew_grid(ctx, (int64_t)sz), 256, 0, Xs.back().p, 1.0, F.p, -1.0, F.p + sz, (int64_t)sz);   // :106
         double hinfo[2] = {0, 0};
         int hneed = 0;
-        if (j > 2) {
-            // || Xm - pad(Xm(j-2)) ||_2 < tol   (:112-114): Frobenius norm first, Lanczos only inside the band
-            const int ctas = (int)std::min<int64_t>(256, std::max<int64_t>(1, ceil_div((int64_t)sz, 256)));
-            KR_LAUNCH(ctx, diff_sym_kernel, ctas, 256, 0, Xs.back().p, nn, Xs[Xs.size() - 3].p, Xdim[Xdim.size() - 3], D.p, part.p);
-            KR_LAUNCH(ctx, stop_band_kernel, 1, 1, 0, part.p, ctas, nn, tol, info_dev.p, need.p);
-            if (Q.count < (size_t)nn * (NRM2_STEPS + 1)) Q.reset(ctx, (size_t)nn * (NRM2_STEPS + 1));
-            KR_LAUNCH(ctx, sym_norm2_kernel, 1, 256, 0, D.p, nn, Q.p, need.p, info_dev.p + 1);
-            KR_CUDA(cudaMemcpyAsync(hinfo, info_dev.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            KR_CUDA(cudaMemcpyAsync(&hneed, need.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            ew.begin(ctx, attempt == 1);
+            symfun_batched(ctx, SG.p, nn, 2, fun, ws.norm_bound, F.p, ew);
+            KR_LAUNCH(ctx, axpby_kernel, ew_grid(ctx, (int64_t)sz), 256, 0, Xs.back().p, 1.0, F.p, -1.0, F.p + sz, (int64_t)sz);   // :106
+            if (j > 2) {
+                // || Xm - pad(Xm(j-2)) ||_2 < tol   (:112-114): Frobenius norm first, Lanczos only inside the band
+                const int ctas = (int)std::min<int64_t>(256, std::max<int64_t>(1, ceil_div((int64_t)sz, 256)));
+                KR_LAUNCH(ctx, diff_sym_kernel, ctas, 256, 0, Xs.back().p, nn, Xs[Xs.size() - 3].p, Xdim[Xdim.size() - 3], D.p, part.p);
+                KR_LAUNCH(ctx, stop_band_kernel, 1, 1, 0, part.p, ctas, nn, tol, info_dev.p, need.p);
+                if (Q.count < (size_t)nn * (NRM2_STEPS + 1)) Q.reset(ctx, (size_t)nn * (NRM2_STEPS + 1));
+                KR_LAUNCH(ctx, sym_norm2_kernel, 1, 256, 0, D.p, nn, Q.p, need.p, tol, info_dev.p + 1);
+                KR_CUDA(cudaMemcpyAsync(hinfo, info_dev.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                KR_CUDA(cudaMemcpyAsync(&hneed, need.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            ew.enqueue_readback(ctx);
+            sync_lucky(st);                                   // the step's only synchronisation
+            if (ew.accept()) break;
         }
-        sync_lucky(st);                                       // the step's only synchronisation
         if (wide_prof().on) { wide_prof().fun += WideProf::now() - t1; wide_prof().n_fun++; wide_prof().max_dim = std::max(wide_prof().max_dim, nn); }
         info.lucky = st->lucky;
         bool done = false;
@@ -706,6 +716,174 @@ __global__ void colabs_rowsum_kernel(CsrDevView At, double* __restrict__ x) {
 }
 __global__ void vec_scale_kernel(double* __restrict__ x, int64_t n, double f) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= f;
+}
+
+// Leading eigenvector by power iteration, whole loop in ONE CTA (small graphs: launch-bound otherwise).
+//   mode 0 ('eig', functions/compute_centrality.m:15-17): y = A (A x) / ||.||  - two products per test so that a
+//           bipartite-like oscillation does not fool the stopping rule;
+//   mode 1 ('pr', :20-26): y = alpha A D x + (1 - alpha) sum(x) / n, D = diag(1 ./ sum(A)), alpha = 0.85.
+// Stops when || y/||y|| - x ||_2 < tol.  out = {iterations, converged}.
+__global__ void __launch_bounds__(1024)
+power_iteration_small_kernel(CsrDevView A, int mode, double tol, int maxit, double* __restrict__ x, double* __restrict__ y,
+                             double* __restrict__ dinv, double* __restrict__ out) {
+    __shared__ double red[32];
+    __shared__ double s_val;
+    const int n = A.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto bsum = [&](double v) -> double {
+        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 32; ++w) s += red[w];
+            s_val = s;
+        }
+        __syncthreads();
+        return s_val;
+    };
+    auto spmv_cta = [&](const double* in, double* o, const double* scale) {
+        for (int g = warp; g < n; g += 32) {
+            const int p0 = A.row_ptr[g], p1 = A.row_ptr[g + 1];
+            double s = 0.0;
+            for (int p = p0 + lane; p < p1; p += 32) {
+                const int c = A.col[p];
+                s += (A.val ? A.val[p] : A.uval) * (scale ? in[c] * scale[c] : in[c]);
+            }
+            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) o[A.row_order[g]] = s;
+        }
+        __syncthreads();
+    };
+    if (mode == 1) {        // dinv = 1 ./ sum(A) (column sums = row sums of the symmetric A)
+        for (int g = warp; g < n; g += 32) {
+            double s = 0.0;
+            for (int p = A.row_ptr[g] + lane; p < A.row_ptr[g + 1]; p += 32) s += A.val ? A.val[p] : A.uval;
+            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) dinv[A.row_order[g]] = 1.0 / s;
+        }
+    }
+    const double x0 = 1.0 / sqrt((double)n);
+    for (int i = tid; i < n; i += 1024) x[i] = x0;
+    __syncthreads();
+    int it = 0, conv = 0;
+    while (it < maxit) {
+        if (mode == 0) {
+            spmv_cta(x, y, nullptr);
+            // x is still needed for the test: the second product lands in a third vector = dinv (unused in mode 0)
+            spmv_cta(y, dinv, nullptr);
+        } else {
+            double sx = 0.0;
+            for (int i = tid; i < n; i += 1024) sx += x[i];
+            sx = bsum(sx);
+            spmv_cta(x, y, dinv);
+            const double add = (1.0 - 0.85) * sx / (double)n;
+            for (int i = tid; i < n; i += 1024) y[i] = 0.85 * y[i] + add;
+            __syncthreads();
+        }
+        double* z = mode == 0 ? dinv : y;
+        double a = 0.0;
+        for (int i = tid; i < n; i += 1024) a += z[i] * z[i];
+        const double nrm = sqrt(bsum(a));
+        if (!(nrm > 0.0)) break;
+        double d = 0.0;
+        for (int i = tid; i < n; i += 1024) {
+            const double v = z[i] / nrm;
+            const double e = v - x[i];
+            d += e * e;
+            z[i] = v;
+        }
+        d = sqrt(bsum(d));
+        for (int i = tid; i < n; i += 1024) x[i] = z[i];
+        __syncthreads();
+        ++it;
+        if (d < tol) { conv = 1; break; }
+    }
+    if (tid == 0) { out[0] = (double)it; out[1] = (double)conv; }
+}
+
+// one step of the same iteration with grid-wide kernels (large graphs); the host reads the distance every few steps
+__global__ void pr_combine_kernel(double* __restrict__ y, int64_t n, const double* __restrict__ sumx) {
+    const double add = (1.0 - 0.85) * sumx[0] / (double)n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = 0.85 * y[i] + add;
+}
+__global__ void vec_mul_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ o, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) o[i] = a[i] * b[i];
+}
+__global__ void vec_recip_kernel(double* __restrict__ a, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = 1.0 / a[i];
+}
+// z <- z / sqrt(*n2); partial[b] = sum (z - x)^2; x <- z
+__global__ void __launch_bounds__(256)
+normalize_diff_kernel(double* __restrict__ z, double* __restrict__ x, int64_t n, const double* __restrict__ n2,
+                      double* __restrict__ partial) {
+    __shared__ double red[8];
+    const double nrm = sqrt(n2[0]);
+    const double f = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    double d = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double v = z[i] * f, e = v - x[i];
+        d += e * e;
+        x[i] = v;
+    }
+    for (int off = 16; off; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) d += red[w];
+        partial[blockIdx.x] = d;
+    }
+}
+
+struct CentralityInfo { int64_t iters = 0; int converged = 0; };
+// c = |leading eigenvector| (unit 2-norm), mode 0 'eig' / mode 1 'pr'
+inline CentralityInfo leading_vector_dev(kr_ctx* ctx, const kr_matrix* M, int mode, double tol, int64_t maxit, double* c_host) {
+    const int64_t n = M->dev.n;
+    CentralityInfo info;
+    if (n == 0) return info;
+    if (mode == 1 && !M->symmetric) fail(KR_ERR_UNSUPPORTED, "compute_centrality 'pr': the device path expects a symmetric A");
+    DevBuf<double> x(ctx, n), y(ctx, n), z(ctx, n), sc(ctx, 4), part(ctx, VEC_RED_CTAS);
+    static const int64_t small_nnz = [] { const char* e = getenv("KR_NORMEST_SMALL_NNZ"); return e ? atoll(e) : (int64_t)400000; }();
+    if (M->dev.nnz <= small_nnz) {
+        KR_LAUNCH(ctx, power_iteration_small_kernel, 1, 1024, 0, M->dev.view(), mode, tol, (int)std::min<int64_t>(maxit, 1 << 30), x.p, y.p, z.p, sc.p);
+        double h[2];
+        sc.download(h, 2);
+        info.iters = (int64_t)h[0];
+        info.converged = (int)h[1];
+    } else {
+        const int eg = ew_grid(ctx, n);
+        const int ctas = (int)std::min<int64_t>(VEC_RED_CTAS, std::max<int64_t>(1, ceil_div(n, 256)));
+        KR_LAUNCH(ctx, fill_kernel, eg, 256, 0, x.p, n, 1.0 / std::sqrt((double)n));
+        DevBuf<double> dinv;
+        if (mode == 1) {
+            dinv.reset(ctx, n);
+            KR_LAUNCH(ctx, colabs_rowsum_kernel, (int)ceil_div(n * 8, 256), 256, 0, M->dev.view(), dinv.p);
+            KR_LAUNCH(ctx, vec_recip_kernel, eg, 256, 0, dinv.p, n);
+        }
+        while (info.iters < maxit && !info.converged) {
+            double* out = z.p;
+            if (mode == 0) {
+                spmv(ctx, M->dev, x.p, y.p);
+                spmv(ctx, M->dev, y.p, z.p);
+            } else {
+                vec_reduce<2>(ctx, x.p, x.p, n, part.p, sc.p + 2);           // sum(x): x >= 0 throughout
+                KR_LAUNCH(ctx, vec_mul_kernel, eg, 256, 0, x.p, dinv.p, y.p, n);
+                spmv(ctx, M->dev, y.p, z.p);
+                KR_LAUNCH(ctx, pr_combine_kernel, eg, 256, 0, z.p, n, sc.p + 2);
+            }
+            vec_reduce<0>(ctx, out, out, n, part.p, sc.p);
+            KR_LAUNCH(ctx, normalize_diff_kernel, ctas, 256, 0, out, x.p, n, sc.p, part.p);
+            KR_LAUNCH(ctx, vec_reduce_finish_kernel<0>, 1, 1, 0, part.p, ctas, sc.p + 1);
+            info.iters += 1;
+            double dist = 0;                                             // one scalar per iteration (large graphs only)
+            KR_CUDA(cudaMemcpyAsync(&dist, sc.p + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            KR_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (std::sqrt(dist) < tol) info.converged = 1;
+        }
+    }
+    std::vector<double> h = x.to_host();
+    for (int64_t i = 0; i < n; ++i) c_host[i] = std::abs(h[(size_t)i]);
+    return info;
 }
 
 // MATLAB normest(S, tol): power iteration on S'S from the column abs-sums

@@ -181,11 +181,15 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 inline void* kr_ctx::alloc(size_t bytes) {
     size_t b = kr::bucket(bytes);
+    // debugging aid (KR_POOL_POISON=1): every buffer handed out is filled with NaN bit patterns first, so a kernel
+    // that reads memory it (or a predecessor) never wrote turns the result into NaN instead of a plausible number
+    static const bool poison = getenv("KR_POOL_POISON") != nullptr;
     auto it = pool.find(b);
     if (it != pool.end()) {
         void* p = it->second;
         pool.erase(it);
         pool_bytes -= b;
+        if (poison) cudaMemsetAsync(p, 0xFF, b, stream);
         return p;
     }
     void* p = nullptr;
@@ -199,6 +203,7 @@ inline void* kr_ctx::alloc(size_t bytes) {
             kr::fail(KR_ERR_NOMEM, "device allocation of %zu bytes failed: %s", b, cudaGetErrorString(e));
         }
     }
+    if (poison) cudaMemsetAsync(p, 0xFF, b, stream);
     return p;
 }
 

@@ -13,6 +13,7 @@
 // SPMM_LONG_ROW get a tile (and a whole CTA) of their own.
 #pragma once
 #include <algorithm>
+#include <map>
 #include <numeric>
 
 #include "common.cuh"
@@ -43,6 +44,15 @@ struct CsrDevView {
     const int* __restrict__ row_order;
     const int* __restrict__ row_pos;  // inverse of row_order: stored position of original row i
     const RowTile* __restrict__ tiles;
+    // pending edge edits (kr_matrix_set_edges between two rounds of the greedy loop, functions/krylov_miobi.m:127-135):
+    // A = stored CSR + sum of delta entries.  Sorted by stored row; dl_tile_begin[t] .. [t+1] are tile t's entries,
+    // dl_row_begin-less lookups scan that (tiny) range.  All null when there is nothing pending.
+    const int* __restrict__ dl_tile_begin;   // [ntiles + 1]
+    const int* __restrict__ dl_rowlocal;     // row index inside its tile
+    const int* __restrict__ dl_pos;          // stored row position
+    const int* __restrict__ dl_col;          // column (original numbering)
+    const double* __restrict__ dl_val;       // new value - stored value
+    int dl_count;
 };
 
 #ifndef KR_SPMM_CAP
@@ -60,6 +70,11 @@ struct CsrDev {
     DevBuf<int> row_ptr, col, row_order, row_pos;
     DevBuf<double> val;
     DevBuf<RowTile> tiles;
+    DevBuf<int> dl_tile_begin, dl_rowlocal, dl_pos, dl_col;
+    DevBuf<double> dl_val;
+    int dl_count = 0;
+    std::vector<RowTile> tiles_host;          // host copies for locating an edited row's tile
+    std::vector<int> row_pos_host;
     int ntiles = 0;
     bool pattern_only = false;
     double uval = 1.0;
@@ -74,6 +89,13 @@ struct CsrDev {
         v.row_order = row_order.p;
         v.row_pos = row_pos.p;
         v.tiles = tiles.p;
+        const bool dl = dl_count > 0;
+        v.dl_tile_begin = dl ? dl_tile_begin.p : nullptr;
+        v.dl_rowlocal = dl ? dl_rowlocal.p : nullptr;
+        v.dl_pos = dl ? dl_pos.p : nullptr;
+        v.dl_col = dl ? dl_col.p : nullptr;
+        v.dl_val = dl ? dl_val.p : nullptr;
+        v.dl_count = dl_count;
         return v;
     }
 };
@@ -220,6 +242,9 @@ inline void upload_csr(kr_ctx* ctx, const CsrHost& H, CsrDev& D) {
     for (int64_t s = 0; s < n; ++s) pos[(size_t)P.order[(size_t)s]] = (int)s;
     D.row_pos.reset(ctx, std::max<int64_t>(n, 1));
     if (n) D.row_pos.upload(pos.data(), n);
+    D.tiles_host = P.tiles;
+    D.row_pos_host = pos;
+    D.dl_count = 0;
     D.tiles.reset(ctx, std::max<size_t>(P.tiles.size(), 1));
     if (!P.tiles.empty()) D.tiles.upload(P.tiles.data(), P.tiles.size());
     KR_CUDA(cudaStreamSynchronize(ctx->stream));   // host staging vectors die here
@@ -229,7 +254,8 @@ inline void upload_csr(kr_ctx* ctx, const CsrHost& H, CsrDev& D) {
 
 struct kr_matrix {
     kr_ctx* ctx = nullptr;
-    kr::CsrHost host;          // kept for kr_matrix_set_edges and host-side glue
+    kr::CsrHost host;          // kept for kr_matrix_set_edges and host-side glue (the STORED matrix: pending edits not applied)
+    std::map<std::pair<int64_t, int64_t>, double> pending;    // (row, col) -> new value - stored value (both triangles)
     kr::CsrDev dev;            // A
     kr::CsrDev devT;           // A' (only when !symmetric)
     bool symmetric = true;
@@ -295,4 +321,104 @@ inline void analyse_and_upload(kr_matrix* M, bool keep_symmetric = false) {
     else { M->devT = CsrDev(); }
 }
 
+// stored value of A(i, j) in the host CSR (0 when absent)
+inline double host_entry(const CsrHost& H, int64_t i, int64_t j) {
+    const int32_t* b = H.col.data() + H.row_ptr[i];
+    const int32_t* e = H.col.data() + H.row_ptr[i + 1];
+    const int32_t* q = std::lower_bound(b, e, (int32_t)j);
+    return (q != e && *q == (int32_t)j) ? H.val[(size_t)(q - H.col.data())] : 0.0;
+}
+
+constexpr size_t KR_MAX_PENDING = 8192;      // beyond this many delta entries the CSR is re-built
+
+// ship the pending delta entries to the device (a few hundred bytes + one int per tile)
+inline void upload_pending(kr_matrix* M) {
+    kr_ctx* ctx = M->ctx;
+    CsrDev& D = M->dev;
+    struct Ent { int pos, col; double val; };
+    std::vector<Ent> ents;
+    ents.reserve(M->pending.size());
+    for (auto& kv : M->pending)
+        if (kv.second != 0.0) ents.push_back(Ent{D.row_pos_host[(size_t)kv.first.first], (int)kv.first.second, kv.second});
+    std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.pos != b.pos ? a.pos < b.pos : a.col < b.col; });
+    D.dl_count = (int)ents.size();
+    if (ents.empty()) return;
+    const int nt = D.ntiles;
+    std::vector<int> tb((size_t)nt + 1, 0), rl(ents.size()), ps(ents.size()), cl(ents.size());
+    std::vector<double> vl(ents.size());
+    size_t t = 0;
+    for (size_t e = 0; e < ents.size(); ++e) {
+        while (t + 1 < D.tiles_host.size() && D.tiles_host[t + 1].start <= ents[e].pos) ++t;
+        tb[t + 1] += 1;
+        rl[e] = ents[e].pos - D.tiles_host[t].start;
+        ps[e] = ents[e].pos;
+        cl[e] = ents[e].col;
+        vl[e] = ents[e].val;
+    }
+    for (int q = 0; q < nt; ++q) tb[(size_t)q + 1] += tb[(size_t)q];
+    if (D.dl_tile_begin.count < tb.size()) D.dl_tile_begin.reset(ctx, tb.size());
+    if (D.dl_rowlocal.count < ents.size()) {
+        const size_t cap = std::max<size_t>(256, 2 * ents.size());
+        D.dl_rowlocal.reset(ctx, cap);
+        D.dl_pos.reset(ctx, cap);
+        D.dl_col.reset(ctx, cap);
+        D.dl_val.reset(ctx, cap);
+    }
+    D.dl_tile_begin.upload(tb.data(), tb.size());
+    D.dl_rowlocal.upload(rl.data(), rl.size());
+    D.dl_pos.upload(ps.data(), ps.size());
+    D.dl_col.upload(cl.data(), cl.size());
+    D.dl_val.upload(vl.data(), vl.size());
+    KR_CUDA(cudaStreamSynchronize(ctx->stream));      // host staging vectors die here (a few KB)
+}
+
+// fold the pending edits into the stored CSR (host rebuild + re-analysis + upload): every entry point that reads
+// the CSR outside the SpMM / candidate-seed kernels calls this first; the greedy loop itself never does.
+inline void flush_pending(kr_matrix* M) {
+    if (M->pending.empty()) return;
+    CsrHost& H = M->host;
+    const int64_t n = H.n;
+    std::map<int64_t, std::map<int32_t, double>> edits;
+    for (auto& kv : M->pending) edits[kv.first.first][(int32_t)kv.first.second] = kv.second;
+    std::map<int64_t, std::vector<std::pair<int32_t, double>>> rebuilt;
+    for (auto& ed : edits) {
+        const int64_t i = ed.first;
+        std::map<int32_t, double> row;
+        for (int64_t p = H.row_ptr[i]; p < H.row_ptr[i + 1]; ++p) row[H.col[p]] = H.val[p];
+        for (auto& kv : ed.second) row[kv.first] += kv.second;               // stored + delta = new value
+        auto& out = rebuilt[i];
+        for (auto& kv : row)
+            if (kv.second != 0.0) out.emplace_back(kv.first, kv.second);     // MATLAB sparse assignment of 0 removes the entry
+    }
+    CsrHost N;
+    N.n = n;
+    N.row_ptr.assign(n + 1, 0);
+    {
+        auto it = rebuilt.begin();
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t len = H.row_ptr[i + 1] - H.row_ptr[i];
+            if (it != rebuilt.end() && it->first == i) { len = (int64_t)it->second.size(); ++it; }
+            N.row_ptr[i + 1] = N.row_ptr[i] + len;
+        }
+    }
+    N.col.resize((size_t)N.row_ptr[n]);
+    N.val.resize((size_t)N.row_ptr[n]);
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t i = 0; i < n; ++i) {
+        auto it = rebuilt.find(i);
+        if (it == rebuilt.end()) {
+            std::copy(H.col.begin() + H.row_ptr[i], H.col.begin() + H.row_ptr[i + 1], N.col.begin() + N.row_ptr[i]);
+            std::copy(H.val.begin() + H.row_ptr[i], H.val.begin() + H.row_ptr[i + 1], N.val.begin() + N.row_ptr[i]);
+        } else {
+            int64_t w = N.row_ptr[i];
+            for (auto& kv : it->second) { N.col[(size_t)w] = kv.first; N.val[(size_t)w] = kv.second; ++w; }
+        }
+    }
+    H = std::move(N);
+    M->pending.clear();
+    analyse_and_upload(M, /*keep_symmetric=*/true);
+}
+inline void materialize(const kr_matrix* M) { flush_pending(const_cast<kr_matrix*>(M)); }
+
 }  // namespace kr
+

@@ -199,6 +199,35 @@ pair_seed_kernel(CsrDevView A, PairState st, double* __restrict__ P, double* __r
     }
     seed_reduce<6>(acc, red);
     if (threadIdx.x == 0) {
+        // pending edge edits (kr_matrix_set_edges): A = stored CSR + delta entries.  The rows of i and j are merged
+        // here, serially (a handful of entries): W1 and its Gram follow the EFFECTIVE columns of A.
+        if (A.dl_count > 0) {
+            __threadfence_block();
+            for (int side = 0; side < 2; ++side) {
+                const int pos = side == 0 ? si : sj, oc = side == 0 ? o0 : o1;
+                int lo = 0, hi = A.dl_count;                      // first entry of stored row `pos`
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (A.dl_pos[mid] < pos) lo = mid + 1; else hi = mid; }
+                for (int e = lo; e < A.dl_count && A.dl_pos[e] == pos; ++e) {
+                    const int r = A.dl_col[e];
+                    const double d = A.dl_val[e];
+                    if (r == i || r == j) {                       // entries of U'AU
+                        if (side == 0 && r == i) acc[3] += d;
+                        else if (side == 1 && r == j) acc[5] += d;
+                        else if (side == 0) acc[4] += d;          // a_ij (the (j, i) twin carries the same delta)
+                        continue;
+                    }
+                    double* ci = Cp + (int64_t)r * PW + o0;
+                    double* cj = Cp + (int64_t)r * PW + o1;
+                    const double oi = *ci, oj = *cj;
+                    (side == 0 ? *ci : *cj) += d;
+                    const double ni = *ci, nj = *cj;
+                    acc[0] += ni * ni - oi * oi;
+                    acc[1] += ni * nj - oi * oj;
+                    acc[2] += nj * nj - oj * oj;
+                    (void)oc;
+                }
+            }
+        }
         Pp[(int64_t)i * PW + o0] = 1.0;
         Pp[(int64_t)j * PW + o1] = 1.0;
         st.G3[h * 4 + 0] = acc[0];

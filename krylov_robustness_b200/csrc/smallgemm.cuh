@@ -14,7 +14,7 @@ namespace kr {
 // C[b] = alpha * A[b] * B[b] + beta * C[b]; column-major, batch strides in elements.  64 x 64 tile per CTA,
 // 8 warps as 2 (m) x 4 (n), warp tile 32 x 16, K slab 16.  If sq_count != nullptr and sq_index >= *sq_count the
 // product is skipped and C = A (a squaring that is not needed).
-constexpr int SG_T = 64, SG_K = 16;
+constexpr int SG_T = 64, SG_K = 32;
 constexpr int SG_AS = SG_T + 4;     // As[k][m]
 constexpr int SG_BS = SG_K + 4;     // Bs[n][k]
 
@@ -97,7 +97,7 @@ inline void sgemm(kr_ctx* ctx, int m, int n, int k, double alpha, const double* 
 // ------------------------------------------------------------------------------------ f(S)
 struct ExpmCtl {
     int s;              // squarings actually needed
-    int pad;
+    int clamped;        // sticky: some evaluation needed more squarings than were enqueued (the caller re-runs it)
     double scale;       // 2^-s
     double norm1;       // max over the batch of ||S||_1
 };
@@ -119,7 +119,7 @@ __global__ void expm_decide_kernel(unsigned long long* __restrict__ bits, double
     *bits = 0ull;                                  // ready for the next call
     int s = 0;
     if (nrm > theta) s = (int)ceil(log2(nrm / theta));
-    if (s > s_max) s = s_max;                      // cannot happen when the host bound is valid
+    if (s > s_max) { s = s_max; ctl->clamped = 1; }   // only possible with a hint-based s_max (ExpmWork::hint)
     ctl->s = s;
     ctl->scale = ldexp(1.0, -s);
     ctl->norm1 = nrm;
@@ -176,6 +176,29 @@ struct ExpmWork {
     DevBuf<double> pw, t0, t1, t2, neg;
     DevBuf<ExpmCtl> ctl;
     DevBuf<unsigned long long> bits;
+    // The squarings are enqueued before ||S||_1 is known on the host.  The rigorous bound (sqrt(n) ||S||_2) over-
+    // estimates by 4-6 squarings on the reference's graphs (each a wasted launch); callers that synchronise once per
+    // Krylov step anyway pass the previous step's measured norm as a hint (the projected matrices only grow by a
+    // block per step) and re-run the evaluation with the rigorous bound in the rare case the hint was too small.
+    double hint = -1.0;             // last measured ||S||_1 (host), < 0: none
+    ExpmCtl host_ctl;
+    void begin(kr_ctx* ctx, bool rigorous) {
+        if (!ctl.p) {
+            ctl.reset(ctx, 1);
+            bits.reset(ctx, 1);
+            bits.zero();
+        }
+        ctl.zero();
+        if (rigorous) hint = -1.0;
+    }
+    void enqueue_readback(kr_ctx* ctx) {
+        KR_CUDA(cudaMemcpyAsync(&host_ctl, ctl.p, sizeof(ExpmCtl), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    bool accept() {                 // after the stream has been synchronised
+        if (host_ctl.clamped) { hint = -1.0; return false; }
+        hint = host_ctl.norm1;
+        return true;
+    }
 };
 
 inline int ew_grid(kr_ctx* ctx, int64_t total) {
@@ -189,18 +212,15 @@ inline void expm_batched(kr_ctx* ctx, const double* S, int nn, int batch, double
     const int64_t mat = (int64_t)nn * nn, total = mat * batch;
     if (total == 0) return;
     // ||S||_1 <= sqrt(nn) ||S||_2
-    const double b1 = std::sqrt((double)nn) * std::max(norm_bound, 0.0);
+    double b1 = std::sqrt((double)nn) * std::max(norm_bound, 0.0);
+    if (w.hint >= 0.0) b1 = std::min(b1, 4.0 * w.hint + 1e-300);
     int s_max = b1 > EXPM_THETA18 ? (int)std::ceil(std::log2(b1 / EXPM_THETA18)) + 1 : 0;
     s_max = std::min(s_max, 60);
     if (w.pw.count < (size_t)(6 * total)) w.pw.reset(ctx, (size_t)(6 * total));
     if (w.t0.count < (size_t)total) w.t0.reset(ctx, (size_t)total);
     if (w.t1.count < (size_t)total) w.t1.reset(ctx, (size_t)total);
     if (w.t2.count < (size_t)total) w.t2.reset(ctx, (size_t)total);
-    if (!w.ctl.p) {
-        w.ctl.reset(ctx, 1);
-        w.bits.reset(ctx, 1);
-        w.bits.zero();
-    }
+    if (!w.ctl.p) w.begin(ctx, false);
     const int g = ew_grid(ctx, total);
     double* X1 = w.pw.p;
     auto P = [&](int p) { return w.pw.p + (int64_t)(p - 1) * total; };
@@ -260,7 +280,10 @@ trace_diff_kernel(const double* __restrict__ F1, const double* __restrict__ F0, 
 constexpr int NRM2_STEPS = 48;
 __global__ void __launch_bounds__(256)
 sym_norm2_kernel(const double* __restrict__ D, int nn, double* __restrict__ Q /* nn x (NRM2_STEPS+1) scratch */,
-                 const int* __restrict__ need, double* __restrict__ out) {
+                 const int* __restrict__ need, double tol, double* __restrict__ out) {
+    // Every Lanczos vector q_j is a unit vector, so ||D q_j|| <= ||D||_2: as soon as one of them reaches tol the
+    // test "||D||_2 < tol" is decided (false) and the kernel stops - the usual case inside the Frobenius band.
+    // Only a step that really has converged runs the full recurrence (once per fun_update call).
     if (need && !*need) return;
     __shared__ double red[256];
     __shared__ double al[NRM2_STEPS], be[NRM2_STEPS + 1], dl[NRM2_STEPS + 1];
@@ -321,6 +344,14 @@ sym_norm2_kernel(const double* __restrict__ D, int nn, double* __restrict__ Q /*
         if (tid == 0) { al[j] = a; be[j + 1] = b; }
         m = j + 1;
         __syncthreads();
+        {
+            const double bp = j > 0 ? be[j] : 0.0;
+            const double lb = sqrt(a * a + b * b + bp * bp);    // = ||D q_j|| (three-term recurrence)
+            if (lb >= tol) {
+                if (tid == 0) out[0] = lb;
+                return;
+            }
+        }
         if (!(b > 1e-300) || b < 1e-15 * fabs(al[0])) break;
         for (int i = tid; i < nn; i += 256) w[i] /= b;
         __syncthreads();

@@ -502,7 +502,8 @@ __device__ __forceinline__ Vec<CPL> gather_accumulate(int p_first, int p_end, in
 template <int L, bool HAS_VAL, int U, class Epi>
 __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict__ srp, const int* __restrict__ srid,
                                           const int* __restrict__ scol, const double* __restrict__ sval,
-                                          const double* __restrict__ Xp, double uval, Epi& epi) {
+                                          const double* __restrict__ Xp, double uval, Epi& epi, const CsrDevView& A,
+                                          int e0, int e1) {
     constexpr int CPL = Epi::CPL;
     constexpr int LP = PW / CPL;        // lanes per row-tile
     constexpr int S = L / LP;           // nonzero slots per row
@@ -546,6 +547,15 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict
 #pragma unroll
             for (int i = 0; i < CPL; ++i) acc.v[i] *= uval;
         }
+        if (e1 > e0 && emit) {            // pending edge edits of this tile (kr_matrix_set_edges): y_row += delta * x_col
+            for (int e = e0; e < e1; ++e)
+                if (A.dl_rowlocal[e] == rr) {
+                    const Vec<CPL> x = ld_x<CPL>(xs + (int64_t)A.dl_col[e] * PW);
+                    const double d = A.dl_val[e];
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) acc.v[i] = fma(d, x.v[i], acc.v[i]);
+                }
+        }
         const unsigned m = __ballot_sync(0xffffffffu, emit);
         if (emit) epi.row(row, sub, acc, m);
     }
@@ -572,6 +582,8 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
     const int pb = __ldg(A.row_ptr + t.start);
     const int nz = __ldg(A.row_ptr + t.start + t.count) - pb;
     const bool long_row = t.lanes_log2 == 6;   // class 6: one row, whole CTA
+    const int e0 = A.dl_tile_begin ? A.dl_tile_begin[tile] : 0;
+    const int e1 = A.dl_tile_begin ? A.dl_tile_begin[tile + 1] : 0;
     Epi epi = epi_proto;
     epi.init(panel, panel_stride);
     const double* Xp = X + (int64_t)panel * panel_stride;
@@ -584,10 +596,10 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
             for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + p);
         __syncthreads();
         switch (t.lanes_log2) {          // slots per row = 1 << lanes_log2, lanes per row = LP << lanes_log2 (<= 32)
-            case 0: spmm_tile<LP, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
-            case 1: spmm_tile<2 * LP, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
-            case 2: spmm_tile<(4 * LP > 32 ? 32 : 4 * LP), HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
-            default: spmm_tile<(8 * LP > 32 ? 32 : 8 * LP), HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi); break;
+            case 0: spmm_tile<LP, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
+            case 1: spmm_tile<2 * LP, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
+            case 2: spmm_tile<(4 * LP > 32 ? 32 : 4 * LP), HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
+            default: spmm_tile<(8 * LP > 32 ? 32 : 8 * LP), HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
         }
     } else {
         // one long row, whole CTA: stage the indices chunk by chunk, SPMM_THREADS / LP nonzero slots
@@ -613,6 +625,14 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
         Vec<CPL> acc;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) acc.v[i] = HAS_VAL ? v[i] : v[i] * A.uval;
+        if (e1 > e0 && emit) {
+            for (int e = e0; e < e1; ++e) {      // a long-row tile holds one row: every entry is its
+                const Vec<CPL> x = ld_x<CPL>(Xp + sub * CPL + (int64_t)A.dl_col[e] * PW);
+                const double d = A.dl_val[e];
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) acc.v[i] = fma(d, x.v[i], acc.v[i]);
+            }
+        }
         const unsigned m = __ballot_sync(0xffffffffu, emit);
         if (emit) epi.row(row, sub, acc, m);
         __syncthreads();                               // red[] is reused by epi.finish

@@ -236,8 +236,8 @@ inline void ts_update(kr_ctx* ctx, const PanelList& V, const PanelList& W, int64
 // Pass k of the form-Q phase (dorg2r, k = bs-1 .. 0, plus one leading dots-only pass) works the same way with
 // the reflectors read back from the strictly lower part of W.
 constexpr int HQR_MAXB = 128;        // widest block
-constexpr int HQR_THREADS = 256;
-constexpr int HQR_ROWS = 256;        // rows per CTA
+constexpr int HQR_THREADS = 1024;    // 32 warps, one row per warp at a time: the passes are latency-bound (a row's
+constexpr int HQR_ROWS = 128;        // reflector entry is a dependent load), so few rows per warp = 4
 
 struct HqrState {
     double* R;          // [bs*bs]

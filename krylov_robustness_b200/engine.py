@@ -102,6 +102,23 @@ class Matrix:
                                             C.byref(h)))
         self.h = h
 
+    @classmethod
+    def from_csr_arrays(cls, n, indptr, indices, data, ctx=None):
+        """Device matrix straight from CSR arrays (0-based; `data` may be a scalar for a uniform-valued pattern):
+        skips the SciPy conversions of the constructor, which copy the arrays several times - noticeable at
+        2^28 stored entries (config C4)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or Context.default()
+        self.n = int(n)
+        self.shape = (self.n, self.n)
+        rp = np.ascontiguousarray(indptr, dtype=np.int64)
+        ci = np.ascontiguousarray(indices, dtype=np.int64)
+        va = np.full(ci.size, float(data)) if np.isscalar(data) else np.ascontiguousarray(data, dtype=np.float64)
+        h = C.c_void_p()
+        check(self.ctx.lib.kr_matrix_create(self.ctx.h, self.n, int(ci.size), _ptr(rp), _ptr(ci), _ptr(va), C.byref(h)))
+        self.h = h
+        return self
+
     @staticmethod
     def wrap(A, ctx=None):
         return A if isinstance(A, Matrix) else Matrix(A, ctx)

@@ -372,48 +372,32 @@ def edge2low_rank(E, n, sign=-1.0):
     return U, B
 
 
-def compute_centrality(A, kind="eig", tol=1e-13, maxit=5000, block=8):
-    """c = compute_centrality(A,type) for 'eig' (leading eigenvector by power iteration on the device
-    SpMM; functions/compute_centrality.m:15-17 uses eigs) and 'deg' (:18-19).
+def compute_centrality(A, kind="eig", tol=1e-13, maxit=20000):
+    """c = compute_centrality(A,type)  (functions/compute_centrality.m:1-32).
 
-    The iterate stays on the device: `block - 1` double products x <- A(Ax) run back to back without touching the
-    host (growth <= lambda^(2(block-1)), far inside the fp64 range for every graph on this path), then the vector
-    is normalised on the host and ONE more double product decides convergence exactly as the unblocked loop did
-    (||y/||y|| - x|| < tol); two products per test so that bipartite-like oscillation does not fool the rule."""
+    'eig' (:15-17, the reference calls eigs(A,1)) and 'pr' (:20-26, PageRank with alpha = 0.85) are power
+    iterations that run entirely on the device (kr_compute_centrality: one kernel launch for the reference's
+    graph sizes, stopping test included); 'deg' (:18-19) is a column sum; 'exp' (:9-10, diag(expm(A))) goes
+    through function_multiple_entries on the diagonal pairs.  'res' (:11-14) uses an undefined `n` in the
+    reference and raises there too.  Unknown types fall back to 'eig' with the reference's notice (:27-30)."""
     if kind == "deg":
         return np.asarray(sp.csr_matrix(A).sum(axis=0)).ravel()
+    if kind == "res":
+        raise NameError("compute_centrality: 'res' references an undefined variable n in the reference "
+                        "(functions/compute_centrality.m:14)")
     M = _mat(A)
-    lib, ctx = M.ctx.lib, M.ctx
-    n = M.n
-    X, Y = Dense(n, 1, ctx), Dense(n, 1, ctx)
-
-    def double_products(k):
-        for _ in range(k):
-            check(lib.kr_spmm_dev(ctx.h, M.h, X.h, Y.h))
-            check(lib.kr_spmm_dev(ctx.h, M.h, Y.h, X.h))
-
-    x = np.ones((n, 1)) / math.sqrt(n)
-    done, it = False, 0
-    while it < maxit and not done:
-        X.upload(x)
-        double_products(block - 1)
-        xa = X.download()
-        nrm = float(np.linalg.norm(xa))
-        if not np.isfinite(nrm) or nrm == 0.0:        # overflow / annihilated start: fall back to unit steps
-            block = 1
-            if nrm == 0.0:
-                break
-            X.upload(x)
-            xa, nrm = x.copy(), 1.0
-        xa /= nrm
-        X.upload(xa)
-        double_products(1)
-        y = X.download()
-        y /= float(np.linalg.norm(y))
-        done = float(np.linalg.norm(y - xa)) < tol
-        x = y
-        it += block
-    return np.abs(x.ravel())
+    if kind == "exp":
+        idx = np.arange(1, M.n + 1, dtype=np.int64)
+        nrm = normest(M, 1e-2)[0]
+        return function_multiple_entries(M, np.stack([idx, idx], axis=1), "exp", 1e-13 * math.exp(nrm), None)[0]
+    if kind not in ("eig", "pr"):
+        print("#### Centrality set to eig ####")
+        kind = "eig"
+    c = np.zeros(M.n)
+    iters, conv = C.c_int64(), C.c_int()
+    check(M.ctx.lib.kr_compute_centrality(M.ctx.h, M.h, 0 if kind == "eig" else 1, float(tol), int(maxit), _ptr(c),
+                                          C.byref(iters), C.byref(conv)))
+    return c
 
 
 def _tril_edges(A):
@@ -446,24 +430,50 @@ def find_top_edges(A, centrality, num, order="mult"):
 
 
 def find_top_missing_edges(A, centrality, num, order="min"):
-    """E = find_top_missing_edges(A,centrality,num,order)  (functions/find_top_missing_edges.m:1-67),
-    'min' ordering (the one the reference's scripts use)."""
-    if order != "min":
-        raise NotImplementedError("find_top_missing_edges: only the 'min' ordering is provided")
+    """E = find_top_missing_edges(A,centrality,num,order)  (functions/find_top_missing_edges.m:1-67):
+    'min' (:55-65, the ordering the reference's scripts use) and 'mult' (:20-54)."""
     centrality = np.asarray(centrality, dtype=np.float64).ravel()
     indC = np.argsort(-centrality, kind="stable")
     Ac = sp.csc_matrix(A)
-    rows, total, j = [], 0, 2
-    while total < num:
-        col = np.zeros(Ac.shape[0])
+    n = Ac.shape[0]
+
+    def missing_above(j):
+        """nodes ranked before the j-th (1-based) that are NOT adjacent to it, in rank order"""
+        col = np.zeros(n)
         s, e = Ac.indptr[indC[j - 1]], Ac.indptr[indC[j - 1] + 1]
         col[Ac.indices[s:e]] = Ac.data[s:e]
         cand = indC[:j - 1]
-        ind = cand[col[cand] == 0]
-        rows.append(np.stack([ind + 1, np.full(ind.size, indC[j - 1] + 1)], axis=1))
-        total += ind.size
-        j += 1
-    return np.concatenate(rows, axis=0)[:num].astype(np.int64)
+        return cand[col[cand] == 0]
+
+    if order == "min":
+        rows, total, j = [], 0, 2
+        while total < num:
+            ind = missing_above(j)
+            rows.append(np.stack([ind + 1, np.full(ind.size, indC[j - 1] + 1)], axis=1))
+            total += ind.size
+            j += 1
+        return np.concatenate(rows, axis=0)[:num].astype(np.int64)
+    if order != "mult":
+        raise ValueError("find_top_missing_edges: order must be 'mult' or 'min'")
+    if (n * n - Ac.nnz - n) / 2 <= num:
+        # :21-29 returns without assigning E in the reference (an error there as well)
+        raise ValueError("find_top_missing_edges: not enough missing edges for order 'mult'")
+    sc = centrality[indC]
+    # smallest prefix of the ranking that already contains `num` missing edges (:31-37)
+    prefix, found = 2, 0
+    while found < num:
+        found += missing_above(prefix).size
+        prefix += 1
+    prefix -= 1
+    # every pair whose product can beat the weakest pair of that prefix lies among the first N nodes (:39)
+    N = int(np.count_nonzero(sc[0] * sc > sc[prefix - 1] ** 2))
+    S = np.triu(np.outer(sc[:N], sc[:N]))
+    flat = np.argsort(-S.ravel(order="F"), kind="stable")               # sort(S(:), 'descend'): column-major, stable
+    ii, jj = np.unravel_index(flat, S.shape, order="F")
+    sub = Ac[indC[:N], :][:, indC[:N]].toarray()
+    keep = (ii != jj) & (sub[ii, jj] == 0)
+    ii, jj = ii[keep][:num], jj[keep][:num]
+    return np.stack([indC[ii] + 1, indC[jj] + 1], axis=1).astype(np.int64)
 
 
 def _issymmetric(A):

@@ -68,6 +68,47 @@ def rmat_graph(scale=24, nnz=1 << 28, abcd=(0.57, 0.19, 0.19, 0.05), seed=2):
     return _symmetric_from_edges(n, i, j, target_edges=m)
 
 
+def rmat_graph_device(scale, nnz, abcd=(0.57, 0.19, 0.19, 0.05), seed=2, device=0):
+    """Same construction as rmat_graph (mirror, dedup, fixed-stride thinning) with the random bits, the
+    sort / unique and the CSR assembly done by torch on the GPU: the NumPy generator needs > 6 minutes of host time
+    at the full C4 size (scale 24, 2^28 stored entries).  Setup only, never timed.  Returns (indptr, indices) as
+    int64 NumPy arrays of the symmetric 0/1 pattern."""
+    import torch
+    dev = torch.device("cuda", device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    n, m = 1 << scale, nnz // 2
+    draw = int(m * 1.25) + 16
+    a, b, c, _ = abcd
+    i = torch.zeros(draw, dtype=torch.int64, device=dev)
+    j = torch.zeros(draw, dtype=torch.int64, device=dev)
+    for _ in range(scale):
+        r = torch.rand(draw, generator=g, device=dev, dtype=torch.float64)
+        right = ((r >= a) & (r < a + b)) | (r >= a + b + c)
+        down = r >= a + b
+        i = (i << 1) | down.to(torch.int64)
+        j = (j << 1) | right.to(torch.int64)
+    del r, right, down
+    keep = i != j
+    lo, hi = torch.minimum(i, j)[keep], torch.maximum(i, j)[keep]
+    del i, j, keep
+    key = torch.unique(lo * n + hi)
+    del lo, hi
+    if key.numel() > m:
+        sel = torch.linspace(0, key.numel() - 1, m, dtype=torch.float64, device=dev).to(torch.int64)
+        key = key[sel]
+    lo, hi = key // n, key % n
+    full = torch.sort(torch.cat([lo * n + hi, hi * n + lo])).values     # row-major order of both triangles
+    del lo, hi, key
+    rows, cols = full // n, full % n
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    indptr, cols = indptr.cpu().numpy(), cols.cpu().numpy()
+    del full, rows
+    torch.cuda.empty_cache()
+    return indptr, cols
+
+
 def spectral_radius_estimate(A, iters=30):
     """Power-iteration estimate of lambda_max used to scale A so that exp stays in range
     (SURVEY.md 7.2.7)."""

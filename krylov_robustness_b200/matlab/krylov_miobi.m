@@ -15,8 +15,10 @@ if strcmp(miobi, 'break') && nnz(A) < 2*k
 end
 sgn = 1; if strcmp(miobi, 'break'), sgn = -1; end
 rob = 0; edges = zeros(0, 2);
+hA = kr_mex('matrix_create', A);                    % A goes to the device ONCE; the rounds edit it in place
+freeA = onCleanup(@() kr_mex('matrix_free', hA));
 for j = 1:min(k, size(E, 1))
-    vals = kr_mex('trace_fun_update_edges', A, double(E), sgn/rescale, tol, it, 'exp', sgn);   % self loops are not rescaled (:88-94)
+    vals = kr_mex('trace_fun_update_edges', hA, double(E), sgn/rescale, tol, it, 'exp', sgn);   % self loops are not rescaled (:88-94)
     if strcmp(miobi, 'break'), mx = [0 inf]; else, mx = [0 -inf]; end
     for h = 1:size(E, 1)
         if (sgn < 0 && vals(h) < mx(2)) || (sgn > 0 && vals(h) > mx(2)), mx = [h vals(h)]; end
@@ -24,6 +26,7 @@ for j = 1:min(k, size(E, 1))
     chosen = E(mx(1), :);
     E = E([1:mx(1)-1, mx(1)+1:end], :);
     A(chosen(1), chosen(2)) = (sgn > 0); A(chosen(2), chosen(1)) = (sgn > 0);
+    kr_mex('matrix_set_edges', hA, chosen(1), chosen(2), double(sgn > 0));      % :127-135 on the device copy
     edges = [edges; chosen]; rob = rob + mx(2);
 end
 A_new = A;

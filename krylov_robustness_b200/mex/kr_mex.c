@@ -29,11 +29,14 @@ static struct { uint64_t key; mwSize n, nnz; kr_matrix* M; } g_cache[KR_CACHE];
 static int g_next = 0;
 #define KR_MAX_KRYLOV 4096
 static kr_krylov* g_krylov[KR_MAX_KRYLOV];      /* live Krylov handles (freed by 'krylov_free' or at exit) */
+#define KR_MAX_MATS 64
+static kr_matrix* g_mats[KR_MAX_MATS];          /* explicit matrix handles ('matrix_create' / 'matrix_free') */
 
 static void at_exit(void) {
     int i;
     for (i = 0; i < KR_MAX_KRYLOV; ++i) if (g_krylov[i]) { kr_krylov_destroy(g_krylov[i]); g_krylov[i] = NULL; }
     for (i = 0; i < KR_CACHE; ++i) if (g_cache[i].M) { kr_matrix_destroy(g_cache[i].M); g_cache[i].M = NULL; }
+    for (i = 0; i < KR_MAX_MATS; ++i) if (g_mats[i]) { kr_matrix_destroy(g_mats[i]); g_mats[i] = NULL; }
     if (g_ctx) { kr_ctx_destroy(g_ctx); g_ctx = NULL; }
 }
 
@@ -80,13 +83,21 @@ static kr_ctx* ctx(void) {
     return g_ctx;
 }
 
+static kr_matrix* create_matrix(const mxArray* A);
+
+/* The matrix argument of every op: a sparse A (device copy cached by content) or a uint64 handle from
+ * 'matrix_create' (a device-resident matrix that 'matrix_set_edges' edits in place, functions/krylov_miobi.m:127-135). */
 static kr_matrix* matrix_of(const mxArray* A) {
     int i;
     mwSize n, nnz;
     const mwIndex *jc, *ir;
-    int64_t *rp, *ci;
     kr_matrix* M = NULL;
     uint64_t key;
+    if (mxIsUint64(A)) {
+        M = *(kr_matrix**)mxGetData(A);
+        for (i = 0; i < KR_MAX_MATS; ++i) if (M && g_mats[i] == M) return M;
+        mexErrMsgTxt("krylov_b200: stale or foreign matrix handle");
+    }
     if (!mxIsSparse(A) || !mxIsDouble(A)) mexErrMsgTxt("A must be a real sparse double matrix");
     if (mxGetM(A) != mxGetN(A)) mexErrMsgTxt("The matrix A should be square");
     n = mxGetN(A); jc = mxGetJc(A); ir = mxGetIr(A); nnz = jc[n];
@@ -95,15 +106,27 @@ static kr_matrix* matrix_of(const mxArray* A) {
     key = hash_words(key, mxGetPr(A), nnz * sizeof(double));
     for (i = 0; i < KR_CACHE; ++i)
         if (g_cache[i].M && g_cache[i].key == key && g_cache[i].n == n && g_cache[i].nnz == nnz) return g_cache[i].M;
-    rp = (int64_t*)mxMalloc((n + 1) * sizeof(int64_t));
-    ci = (int64_t*)mxMalloc((nnz ? nnz : 1) * sizeof(int64_t));
-    for (i = 0; i <= (int)n; ++i) rp[i] = (int64_t)jc[i];
-    { mwSize p; for (p = 0; p < nnz; ++p) ci[p] = (int64_t)ir[p]; }
-    chk(kr_matrix_create(ctx(), (int64_t)n, (int64_t)nnz, rp, ci, mxGetPr(A), &M));
-    mxFree(rp); mxFree(ci);
+    M = create_matrix(A);
     if (g_cache[g_next].M) kr_matrix_destroy(g_cache[g_next].M);
     g_cache[g_next].key = key; g_cache[g_next].n = n; g_cache[g_next].nnz = nnz; g_cache[g_next].M = M;
     g_next = (g_next + 1) % KR_CACHE;
+    return M;
+}
+
+static kr_matrix* create_matrix(const mxArray* A) {
+    mwSize n, nnz, p;
+    const mwIndex *jc, *ir;
+    int64_t *rp, *ci;
+    kr_matrix* M = NULL;
+    if (!mxIsSparse(A) || !mxIsDouble(A)) mexErrMsgTxt("A must be a real sparse double matrix");
+    if (mxGetM(A) != mxGetN(A)) mexErrMsgTxt("The matrix A should be square");
+    n = mxGetN(A); jc = mxGetJc(A); ir = mxGetIr(A); nnz = jc[n];
+    rp = (int64_t*)mxMalloc((n + 1) * sizeof(int64_t));
+    ci = (int64_t*)mxMalloc((nnz ? nnz : 1) * sizeof(int64_t));
+    for (p = 0; p <= n; ++p) rp[p] = (int64_t)jc[p];
+    for (p = 0; p < nnz; ++p) ci[p] = (int64_t)ir[p];
+    chk(kr_matrix_create(ctx(), (int64_t)n, (int64_t)nnz, rp, ci, mxGetPr(A), &M));
+    mxFree(rp); mxFree(ci);
     return M;
 }
 
@@ -133,7 +156,30 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nrhs < 1 || mxGetString(prhs[0], op, sizeof op)) mexErrMsgTxt("kr_mex('<op>', ...)");
     prhs++; nrhs--;
 
-    if (!strcmp(op, "spmm")) {                                     /* Y = kr_mex('spmm', A, X) */
+    if (!strcmp(op, "matrix_create")) {                            /* h = kr_mex('matrix_create', A) */
+        int i;
+        kr_matrix* M = create_matrix(prhs[0]);
+        for (i = 0; i < KR_MAX_MATS && g_mats[i]; ++i) {}
+        if (i == KR_MAX_MATS) { kr_matrix_destroy(M); mexErrMsgTxt("krylov_b200: too many live matrix handles"); }
+        g_mats[i] = M;
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *(kr_matrix**)mxGetData(plhs[0]) = M;
+    } else if (!strcmp(op, "matrix_free")) {                       /* kr_mex('matrix_free', h)  (idempotent) */
+        int i;
+        kr_matrix* M = *(kr_matrix**)mxGetData(prhs[0]);
+        for (i = 0; i < KR_MAX_MATS; ++i) if (M && g_mats[i] == M) { kr_matrix_destroy(M); g_mats[i] = NULL; }
+    } else if (!strcmp(op, "matrix_set_edges")) {                  /* kr_mex('matrix_set_edges', h, i, j, v): A(i,j) = A(j,i) = v */
+        kr_matrix* M = matrix_of(prhs[0]);
+        mwSize cnt = 0, cj = 0, q;
+        int64_t* ii = to_i64(prhs[1], &cnt);
+        int64_t* jj = to_i64(prhs[2], &cj);
+        double* v = (double*)mxMalloc((cnt ? cnt : 1) * sizeof(double));
+        if (cj != cnt) mexErrMsgTxt("matrix_set_edges: i and j must have the same length");
+        for (q = 0; q < cnt; ++q) v[q] = mxGetNumberOfElements(prhs[3]) == 1 ? mxGetScalar(prhs[3]) : mxGetPr(prhs[3])[q];
+        if (!mxIsUint64(prhs[0])) mexErrMsgTxt("matrix_set_edges needs a handle from matrix_create (a cached copy of a MATLAB matrix must not diverge from it)");
+        chk(kr_matrix_set_edges(M, (int64_t)cnt, ii, jj, v));
+        mxFree(ii); mxFree(jj); mxFree(v);
+    } else if (!strcmp(op, "spmm")) {                              /* Y = kr_mex('spmm', A, X) */
         kr_matrix* M = matrix_of(prhs[0]);
         mwSize n = mxGetM(prhs[1]), k = mxGetN(prhs[1]);
         plhs[0] = mxCreateDoubleMatrix(n, k, mxREAL);

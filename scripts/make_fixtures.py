@@ -37,7 +37,7 @@ from krylov_robustness_b200.datasets import unweighted_adjacency as unweighted  
 def main():
     os.makedirs(OUT, exist_ok=True)
     m = sio.loadmat(os.path.join(REF, "MIOBI Codes", "dt_oregon.mat"), spmatrix=True)
-    for k in ("A0", "A1", "A8"):
+    for k in ("A0", "A1", "A2", "A3", "A4", "A5", "A6", "A7", "A8"):       # all nine (config C1 names dt_oregon.mat as a whole)
         save("oregon_%s" % k, m[k])
     for k in ("Anaheim", "Barcelona", "Rome", "Vermont"):       # Vermont = the largest road network (config C2 at full size)
         p = sio.loadmat(os.path.join(REF, "datasets_paper", "Transport", k + ".mat"), spmatrix=True)

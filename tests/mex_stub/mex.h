@@ -41,6 +41,7 @@ mwIndex* mxGetJc(const mxArray* a);
 mwIndex* mxGetIr(const mxArray* a);
 int mxIsSparse(const mxArray* a);
 int mxIsDouble(const mxArray* a);
+int mxIsUint64(const mxArray* a);
 int mxIsEmpty(const mxArray* a);
 int mxGetString(const mxArray* a, char* buf, mwSize buflen);
 void* mxMalloc(size_t n);

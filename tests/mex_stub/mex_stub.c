@@ -52,6 +52,7 @@ mwIndex* mxGetJc(const mxArray* a) { return a->jc; }
 mwIndex* mxGetIr(const mxArray* a) { return a->ir; }
 int mxIsSparse(const mxArray* a) { return a->sparse; }
 int mxIsDouble(const mxArray* a) { return a->cls == mxDOUBLE_CLASS; }
+int mxIsUint64(const mxArray* a) { return a->cls == mxUINT64_CLASS; }
 int mxIsEmpty(const mxArray* a) { return a->m * a->n == 0; }
 int mxGetString(const mxArray* a, char* buf, mwSize buflen) {
     mwSize len = a->m * a->n;

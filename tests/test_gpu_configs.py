@@ -1,0 +1,111 @@
+"""GPU parity on the BASELINE.json configurations themselves, through the C ABI against the oracle:
+  C1  every graph of `MIOBI Codes/dt_oregon.mat` (A0..A8): trace_exp in parity mode + a 250-candidate 'break' round of
+      greedy_krylov's scoring (Tests/test_unweighted_break.m:15-20: Q = 250, tol = 1e-6 exp(||A||), it = 100)
+  C2  the largest road network (Vermont, n = 95 672): sampled entries of the all-edges gradient
+  C5  candidate edges from find_top_missing_edges on a synthetic power-law graph (n = 60 000), rank-2 updates
+Tolerance: 1e-10 relative, iteration counts and lucky flags equal."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import edge_UB
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def kr():
+    import krylov_robustness_b200 as kr
+    return kr
+
+
+@pytest.fixture(scope="module")
+def O():
+    import oracle
+    return oracle
+
+
+@pytest.mark.parametrize("gname", ["oregon_A2", "oregon_A3", "oregon_A4", "oregon_A5", "oregon_A6", "oregon_A7"])
+def test_c1_oregon_trace_exp_and_break_round(kr, O, graphs, gname):
+    A = graphs(gname)
+    n = A.shape[0]
+    rng = np.random.default_rng(0)
+    probes = [(np.sign(rng.standard_normal((n, 10))), np.sign(rng.standard_normal((n, 10)))) for _ in range(34)]
+    M = kr.Matrix(A)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tr = kr.trace_exp(M, probes)
+        otr = O.trace_exp(A, probes)
+    assert abs(tr - otr) <= RTOL * abs(otr), (tr, otr)
+    nrm, _ = O.normest(A, 1e-2)
+    dn, _ = kr.normest(M, 1e-2)
+    assert abs(dn - nrm) <= 1e-12 * nrm
+    tol = 1e-6 * float(np.exp(nrm))
+    c = O.compute_centrality(A, "eig")
+    E = O.find_top_edges(A, c, 250, "min")
+    x, it, lucky = kr.trace_fun_update_edges(M, E, -1.0, tol, 100, "exp")
+    ox, oit, olk = np.zeros(len(E)), np.zeros(len(E), dtype=int), np.zeros(len(E), dtype=bool)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for h, (i, j) in enumerate(E):
+            U, B = edge_UB(n, int(i), int(j), -1.0)
+            ox[h], oit[h], olk[h] = O.trace_fun_update(A, U, B, tol, 100)
+    assert np.array_equal(it, oit) and np.array_equal(lucky, olk)
+    # candidates with a leaf end point carry the reference's LAPACK completion (tests/test_gpu_krylov.py::
+    # test_trace_fun_update_edges_with_leaf_endpoints): compared at 1e-9 of max(|x|, tol); the rest at 1e-10
+    deg = np.diff(A.indptr)
+    leafy = (deg[E[:, 0] - 1] == 1) | (deg[E[:, 1] - 1] == 1)
+    assert np.all(np.abs(x - ox)[~leafy] <= RTOL * np.abs(ox)[~leafy])
+    assert np.all(np.abs(x - ox)[leafy] <= 1e-9 * np.maximum(np.abs(ox)[leafy], tol))
+    # the round's winner (functions/krylov_miobi.m:112-117: smallest value, first wins) is the same edge
+    assert kr.select_candidate(x, "break")[0] == kr.select_candidate(ox, "break")[0]
+
+
+def test_c5_power_law_missing_edge_candidates(kr, O):
+    from krylov_robustness_b200.graphs import power_law_graph, spectral_radius_estimate
+    n = 60_000
+    A = power_law_graph(n, 1_200_000, 2.2, 7)
+    lam = spectral_radius_estimate(A, 30)
+    A = (A * (1.0 / lam)).tocsr()
+    M = kr.Matrix(A)
+    assert M.info()["pattern_only"]
+    c = O.compute_centrality(A, "eig")
+    cd = kr.compute_centrality(M, "eig")
+    assert np.max(np.abs(cd - c)) <= 1e-9
+    E = O.find_top_missing_edges(A, c, 256, "min")
+    assert np.array_equal(kr.find_top_missing_edges(A, c, 256, "min"), E)
+    tol = 1e-6 * float(np.e)
+    x, it, lucky = kr.trace_fun_update_edges(M, E, 1.0 / lam, tol, 100, "exp")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for h in range(0, 256, 3):
+            U, B = edge_UB(n, int(E[h, 0]), int(E[h, 1]), 1.0 / lam)
+            ox, oit, olk = O.trace_fun_update(A, U, B, tol, 100)
+            assert it[h] == oit and bool(lucky[h]) == bool(olk), (h, it[h], oit)
+            assert abs(x[h] - ox) <= RTOL * abs(ox), (h, x[h], ox)
+
+
+def test_c2_vermont_gradient_entries(kr, O, graphs):
+    """Config C2 at full size: gradient of trace sinh(A + Delta) over edges of the largest road network =
+    entries of cosh(A + Delta) from single-vector Arnoldi spaces (SURVEY.md note N1); a sample of rows against the
+    oracle's function_multiple_entries (0.17 s per distinct row on the host)."""
+    import scipy.sparse as sp
+    A = graphs("transport_Vermont")
+    n = A.shape[0]
+    L = sp.tril(A, -1).tocoo()
+    rng = np.random.default_rng(4)
+    X = 0.1 * L.data * rng.random(L.nnz)
+    D = sp.coo_matrix((X, (L.row, L.col)), shape=(n, n))
+    At = (A + D + D.T).tocsr()
+    nrm, _ = O.normest(At, 1e-2)
+    tol = 1e-8 * float(np.cosh(nrm))
+    sel = rng.choice(L.nnz, 12, replace=False)
+    Om = np.stack([L.row[sel] + 1, L.col[sel] + 1], 1)
+    Xd, itd = kr.function_multiple_entries(At, Om, "cosh", tol, 100)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Xo, ito = O.function_multiple_entries(At, Om, "cosh", tol, 100)
+    assert itd == ito
+    assert np.max(np.abs(Xd - Xo)) <= RTOL * np.max(np.abs(Xo))

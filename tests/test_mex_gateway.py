@@ -90,3 +90,32 @@ def test_gateway_matches_python_binding(tmp_path):
         V, H, params, _ = kr.lanczos_krylov(V, H, params)
         assert tuple(out["lanczos_Vdims"]) == V.shape
         assert np.max(np.abs(out["lanczos_H"].reshape(H.shape, order="F") - H)) <= 1e-13 * np.max(np.abs(H))
+        # fun_update with the basis (Arnoldi variant), U = unit columns at E[:4, 0], B tridiagonal
+        rk = min(4, len(E))
+        U = np.zeros((n, rk)); U[E[:rk, 0] - 1, np.arange(rk)] = 1.0
+        B = np.zeros((rk, rk))
+        for q in range(rk - 1):
+            B[q, q + 1] = B[q + 1, q] = 0.1 * (q + 1)
+        Xm, itf, lk, Um = kr.fun_update(A, U, B, "exp", tol, 100, 0, nargout=4)
+        assert tuple(out["fun_update_info"]) == (itf, float(lk))
+        assert np.max(np.abs(out["fun_update_Xm"].reshape(Xm.shape, order="F") - Xm)) <= 1e-12 * np.max(np.abs(Xm))
+        assert np.max(np.abs(out["fun_update_Um"].reshape(Um.shape, order="F") - Um)) <= 1e-13
+        Xw, dfA = 0.01 * np.arange(1, len(E) + 1), np.full(len(E), 0.5)
+        f2, gr2 = kr.fun_and_grad_krylov_fun(Xw, A, E, "sinh", "cosh", dfA, 1e-8, 100)
+        assert abs(out["fg_f"][0] - f2) <= 1e-12 * abs(f2) and np.max(np.abs(out["fg_gr"] - gr2)) <= 1e-12 * np.max(np.abs(gr2))
+        import scipy.sparse as sp
+        Hes = kr.hessianfcn_exp(np.zeros(len(E)), A, E, 1e-10, 100)
+        assert np.max(np.abs(out["hessian"].reshape(Hes.shape, order="F") - Hes)) <= 1e-12 * np.max(np.abs(Hes))
+        probes = out["mc_probes"].reshape(n, 20, order="F")
+        tr, res, itm = kr.mc_trace(A, n, 1e-3, 30, 1, 0, probes=[(probes[:, :10], probes[:, 10:])])
+        assert out["mc_trace"][2] == itm and abs(out["mc_trace"][0] - tr) <= 1e-12 * abs(tr)
+    # same mxArray, doubled values: a cache keyed on (data pointer, nnz) would have served the old matrix
+    assert np.array_equal(out["spmm_doubled_values"].reshape(n, 3, order="F"), 2.0 * (A @ X))
+    # explicit handle + in-place edge insertion on the device copy == scoring on the edited matrix
+    A2 = sp.lil_matrix(A)
+    A2[E[0, 0] - 1, E[0, 1] - 1] = 1.0
+    A2[E[0, 1] - 1, E[0, 0] - 1] = 1.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x2, _, _ = kr.trace_fun_update_edges(A2.tocsr(), E, 1.0, tol, 100, "exp")
+    assert np.max(np.abs(out["edges_x_after_insert"] - x2) / np.abs(x2)) <= 1e-12
