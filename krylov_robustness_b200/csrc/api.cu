@@ -9,6 +9,7 @@
 #include "theta_table.h"
 #include "smalldense.cuh"
 #include "pairs.cuh"
+#include "pairs_small.cuh"
 #include "expmv.cuh"
 #include "tsdense.cuh"
 #include "smallgemm.cuh"

@@ -86,8 +86,14 @@ __device__ __forceinline__ void mtm2(const double* A, const double* B, double* C
     C[0] = c0; C[1] = c1; C[2] = c2; C[3] = c3;
 }
 
+inline int pair_eig_jacobi() {
+    const char* e = getenv("KR_PAIR_EIG_JACOBI");
+    return (e && atoi(e) != 0) ? 1 : 0;
+}
+
 struct PairState {
     int nslots, it, fun;
+    int eig_jacobi;   // A/B switch (KR_PAIR_EIG_JACOBI=1): projected eigenvalues by cyclic Jacobi instead of tridiagonal multisection
     double tol, b_off;
     // ---- per slot
     long long* cand;  // [nslots] index of the candidate in the caller's list, -1 = idle
@@ -246,18 +252,10 @@ pair_seed_kernel(CsrDevView A, PairState st, double* __restrict__ P, double* __r
     }
 }
 
-// after pass A: h = T' G T (first CGS pass), coefficients of pass B
-__global__ void pair_coef1_kernel(PairState st, const double* __restrict__ G) {
-    int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= st.nslots) return;
-    double* cf = st.coef + (int64_t)h * 12;
-    if (st.flag[h] != PAIR_RUN) {
-        for (int i = 0; i < 12; ++i) cf[i] = 0.0;       // idle slot: its columns stay finite (zero)
-        return;
-    }
-    const double* g = G + (int64_t)h * 8;
-    const double* Tc = st.Tc + h * 4;
-    const double* Tp = st.Tp + h * 4;
+// after pass A: h = T' G T (first CGS pass), coefficients of pass B.  g = {P'Y, C'Y} raw Grams (row-major 2x2 each),
+// cf = {Ma, Mp, Mc}
+__device__ __forceinline__ void pair_coef1_math(const double* g, const double* Tp, const double* Tc, double* cf, double* hp_out,
+                                                double* hc_out) {
     double tmp[4], hp[4], hc[4], Mp[4], Mc[4];
     mm2(g + 4, Tc, tmp);       // (C'Y) Tc
     mtm2(Tc, tmp, hc);         // Tc' (C'Y) Tc
@@ -269,32 +267,151 @@ __global__ void pair_coef1_kernel(PairState st, const double* __restrict__ G) {
         cf[i] = Tc[i];
         cf[4 + i] = Mp[i];
         cf[8 + i] = Mc[i];
-        st.hp[h * 4 + i] = hp[i];
-        st.hc[h * 4 + i] = hc[i];
+        hp_out[i] = hp[i];
+        hc_out[i] = hc[i];
     }
 }
-
-// after pass B: h1 = T' G (W already carries T), h += h1, coefficients of pass C
-__global__ void pair_coef2_kernel(PairState st, const double* __restrict__ G) {
-    int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= st.nslots) return;
-    if (st.flag[h] != PAIR_RUN) return;               // coefficients of an idle slot stay zero
-    const double* g = G + (int64_t)h * 8;
-    const double* Tc = st.Tc + h * 4;
-    const double* Tp = st.Tp + h * 4;
+// after pass B: h1 = T' G (W already carries T), h += h1, coefficients of pass C.  g = {P'W, C'W}
+__device__ __forceinline__ void pair_coef2_math(const double* g, const double* Tp, const double* Tc, double* cf, double* hp_acc,
+                                                double* hc_acc) {
     double hp[4], hc[4], Mp[4], Mc[4];
     mtm2(Tc, g + 4, hc);
     mm2(Tc, hc, Mc);
     mtm2(Tp, g, hp);
     mm2(Tp, hp, Mp);
-    double* cf = st.coef + (int64_t)h * 12;
     cf[0] = 1.0; cf[1] = 0.0; cf[2] = 0.0; cf[3] = 1.0;
     for (int i = 0; i < 4; ++i) {
         cf[4 + i] = Mp[i];
         cf[8 + i] = Mc[i];
-        st.hp[h * 4 + i] += hp[i];
-        st.hc[h * 4 + i] += hc[i];
+        hp_acc[i] += hp[i];
+        hc_acc[i] += hc[i];
     }
+}
+
+__global__ void pair_coef1_kernel(PairState st, const double* __restrict__ G) {
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= st.nslots) return;
+    double* cf = st.coef + (int64_t)h * 12;
+    if (st.flag[h] != PAIR_RUN) {
+        for (int i = 0; i < 12; ++i) cf[i] = 0.0;       // idle slot: its columns stay finite (zero)
+        return;
+    }
+    pair_coef1_math(G + (int64_t)h * 8, st.Tp + h * 4, st.Tc + h * 4, cf, st.hp + h * 4, st.hc + h * 4);
+}
+
+__global__ void pair_coef2_kernel(PairState st, const double* __restrict__ G) {
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= st.nslots) return;
+    if (st.flag[h] != PAIR_RUN) return;               // coefficients of an idle slot stay zero
+    pair_coef2_math(G + (int64_t)h * 8, st.Tp + h * 4, st.Tc + h * 4, st.coef + (int64_t)h * 12, st.hp + h * 4, st.hc + h * 4);
+}
+
+// Thin QR of an n x 2 block from its Gram matrix {g11, g12, g22} (ONE thread).  w1 / w2 point at element (0, column)
+// of the orthogonalised, un-normalised block with row stride ws: only the LAPACK completion of exactly-zero columns
+// touches the data.  Out: R (row-major 2x2, the sub-diagonal block of H) and T with Q = W * T.  Exactly-zero columns
+// follow LAPACK's dgeqr2 / dorg2r (tau = 0 -> the completion is a coordinate vector), functions/lanczos_krylov.m:90.
+__device__ inline void pair_qr_from_gram(double g11, double g12, double g22, double* w1, double* w2, int64_t ws, int64_t n,
+                                         double* R, double* T) {
+    R[0] = R[1] = R[2] = R[3] = 0.0;
+    T[0] = 1.0; T[1] = 0.0; T[2] = 0.0; T[3] = 1.0;
+    if (g11 == 0.0) {
+        // H1 = I, R11 = 0, q1 = e_0
+        const double b0 = w2[0], b1 = n > 1 ? w2[ws] : 0.0;
+        w1[0] = 1.0;
+        R[1] = b0;
+        const double tail = g22 - b0 * b0 - b1 * b1;
+        if (!(tail > 0.0)) {
+            R[3] = b1;                       // tau2 = 0: q2 = e_1
+            w2[0] = 0.0;
+            if (n > 1) w2[ws] = 1.0;
+        } else {
+            const double beta2 = -copysign(sqrt(g22 - b0 * b0), b1);
+            R[3] = beta2;
+            w2[0] = 0.0;                     // q2 = [0; w2(2:n)] / beta2
+            T[3] = 1.0 / beta2;
+        }
+    } else if (g22 == 0.0 && g12 == 0.0) {
+        const double a0 = w1[0], a1 = n > 1 ? w1[ws] : 0.0;
+        const double tail = g11 - a0 * a0;
+        if (!(tail > 0.0)) {
+            R[0] = a0;                       // w1 = a0 e_0: tau1 = 0, q1 = e_0, q2 = e_1
+            w1[0] = 1.0;
+            if (n > 1) w2[ws] = 1.0;
+        } else {
+            const double beta = -copysign(sqrt(g11), a0);
+            const double kappa = a1 / (beta * (a0 - beta));
+            R[0] = beta;
+            T[0] = 1.0 / beta;
+            T[1] = kappa;                    // q2 = kappa*w1 + (e_1 - kappa*beta*e_0)
+            w2[0] = -kappa * beta;
+            if (n > 1) w2[ws] = 1.0;
+        }
+    } else {
+        const double r11 = sqrt(g11);
+        const double r12 = g12 / r11;
+        const double d = g22 - r12 * r12;
+        R[0] = r11;
+        R[1] = r12;
+        T[0] = 1.0 / r11;
+        if (d > 1e-28 * g22) {
+            const double r22 = sqrt(d);
+            R[3] = r22;
+            T[1] = -r12 / (r11 * r22);
+            T[3] = 1.0 / r22;
+        } else {                             // numerically dependent column: deflate it
+            R[3] = 0.0;
+            T[1] = 0.0;
+            T[3] = 0.0;
+        }
+    }
+}
+
+// Xm of step j from the block tridiagonal H (diagonal Hd, super-diagonal Hs, sub-diagonal Hr; [step][4] row-major
+// 2x2 blocks): Gm = H(1:2j, 1:2j) symmetrised, tGm = Gm + Cm, two Jacobi eigen-solves and the trace formula
+// (functions/trace_fun_update.m:72-89).  All NT threads of the CTA call; work = 2*nn*(nn|1) + 2*nn doubles
+// (shared or global), nn = 2j.
+template <int NT>
+__device__ double pair_projected_trace(const double* Hd, const double* Hs, const double* Hr, int j, double b_off, int fun,
+                                       double* work, JacobiShared* sh, bool use_jacobi = false) {
+    const int nn = 2 * j, lda = nn | 1;
+    double* G = work;
+    double* tG = G + nn * lda;
+    double* d1 = tG + nn * lda;
+    double* d2 = d1 + nn;
+    for (int e = threadIdx.x; e < nn * nn; e += NT) {
+        int r = e % nn, c = e / nn;
+        int br = r >> 1, bc = c >> 1, ir = r & 1, ic = c & 1;
+        // H(r, c): block (br, bc); column block bc is step bc+1
+        auto Hval = [&](int rr, int cc, int irr, int icc) -> double {
+            if (rr == cc) return Hd[cc * 4 + irr * 2 + icc];
+            if (rr == cc - 1) return Hs[cc * 4 + irr * 2 + icc];
+            if (rr == cc + 1) return Hr[cc * 4 + irr * 2 + icc];
+            return 0.0;
+        };
+        double v = 0.5 * (Hval(br, bc, ir, ic) + Hval(bc, br, ic, ir));
+        G[r + c * lda] = v;
+        // Cm = B in the leading 2x2 block (V1 = U, so V1'U = I): B = b_off * [0 1; 1 0]
+        double cm = (r < 2 && c < 2 && r != c) ? b_off : 0.0;
+        tG[r + c * lda] = v + cm;
+    }
+    __syncthreads();
+    if (nn <= MS_MAX_N && !use_jacobi) {
+        // LAPACK's route (tridiagonalise + tridiagonal eigenvalues): two warps reduce one matrix each, then all threads
+        // bracket all eigenvalues of both by multisection on Sturm counts (smalldense.cuh)
+        __shared__ double ms_work[2][6 * MS_MAX_N];
+        __shared__ int ms_cnt[NT];
+        const int warp = threadIdx.x >> 5;
+        if (warp == 0) warp_tridiag(tG, nn, lda, ms_work[0], ms_work[0] + MS_MAX_N, ms_work[0] + 2 * MS_MAX_N, ms_work[0] + 3 * MS_MAX_N);
+        else if (warp == 1) warp_tridiag(G, nn, lda, ms_work[1], ms_work[1] + MS_MAX_N, ms_work[1] + 2 * MS_MAX_N, ms_work[1] + 3 * MS_MAX_N);
+        __syncthreads();
+        sturm_multisect2<NT>(ms_work, nn, d1, d2, ms_cnt);
+    } else {
+        block_jacobi<NT>(tG, nn, lda, nullptr, 0, sh);
+        block_sorted_diag<NT>(tG, nn, lda, d1);
+        block_jacobi<NT>(G, nn, lda, nullptr, 0, sh);
+        block_sorted_diag<NT>(G, nn, lda, d2);
+    }
+    return block_trace_formula<NT>(fun, d1, d2, nn, sh->red);
 }
 
 // One CTA per slot in state `mode` (PAIR_NEW: finish step 1 after the seed; PAIR_RUN: finish step step+1 after
@@ -316,63 +433,11 @@ pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict
     double* Hs = st.Hs + ((int64_t)h * it) * 4;
     double* Hr = st.Hr + ((int64_t)h * it) * 4;
     if (threadIdx.x == 0) {
-        const double g11 = G3[h * 4 + 0], g12 = G3[h * 4 + 1], g22 = G3[h * 4 + 2];
         const int c0 = 2 * h, c1 = 2 * h + 1;
         double* w1 = W + (int64_t)(c0 / PW) * n * PW + (c0 % PW);    // element (r, c0) at w1[r*PW]
         double* w2 = W + (int64_t)(c1 / PW) * n * PW + (c1 % PW);
-        double R[4] = {0, 0, 0, 0}, T[4] = {1, 0, 0, 1};
-        // thin QR of the n x 2 block from its Gram matrix; exactly-zero columns follow LAPACK's
-        // dgeqr2/dorg2r (tau = 0 -> the completion is a coordinate vector), functions/lanczos_krylov.m:90
-        if (g11 == 0.0) {
-            // H1 = I, R11 = 0, q1 = e_0
-            const double b0 = w2[0], b1 = n > 1 ? w2[PW] : 0.0;
-            w1[0] = 1.0;
-            R[1] = b0;
-            const double tail = g22 - b0 * b0 - b1 * b1;
-            if (!(tail > 0.0)) {
-                R[3] = b1;                       // tau2 = 0: q2 = e_1
-                w2[0] = 0.0;
-                if (n > 1) w2[PW] = 1.0;
-            } else {
-                const double beta2 = -copysign(sqrt(g22 - b0 * b0), b1);
-                R[3] = beta2;
-                w2[0] = 0.0;                     // q2 = [0; w2(2:n)] / beta2
-                T[3] = 1.0 / beta2;
-            }
-        } else if (g22 == 0.0 && g12 == 0.0) {
-            const double a0 = w1[0], a1 = n > 1 ? w1[PW] : 0.0;
-            const double tail = g11 - a0 * a0;
-            if (!(tail > 0.0)) {
-                R[0] = a0;                       // w1 = a0 e_0: tau1 = 0, q1 = e_0, q2 = e_1
-                w1[0] = 1.0;
-                if (n > 1) w2[PW] = 1.0;
-            } else {
-                const double beta = -copysign(sqrt(g11), a0);
-                const double kappa = a1 / (beta * (a0 - beta));
-                R[0] = beta;
-                T[0] = 1.0 / beta;
-                T[1] = kappa;                    // q2 = kappa*w1 + (e_1 - kappa*beta*e_0)
-                w2[0] = -kappa * beta;
-                if (n > 1) w2[PW] = 1.0;
-            }
-        } else {
-            const double r11 = sqrt(g11);
-            const double r12 = g12 / r11;
-            const double d = g22 - r12 * r12;
-            R[0] = r11;
-            R[1] = r12;
-            T[0] = 1.0 / r11;
-            if (d > 1e-28 * g22) {
-                const double r22 = sqrt(d);
-                R[3] = r22;
-                T[1] = -r12 / (r11 * r22);
-                T[3] = 1.0 / r22;
-            } else {                             // numerically dependent column: deflate it
-                R[3] = 0.0;
-                T[1] = 0.0;
-                T[3] = 0.0;
-            }
-        }
+        double R[4], T[4];
+        pair_qr_from_gram(G3[h * 4 + 0], G3[h * 4 + 1], G3[h * 4 + 2], w1, w2, PW, n, R, T);
         for (int i = 0; i < 4; ++i) {
             Tn[i] = T[i];
             Hd[(j - 1) * 4 + i] = st.hc[h * 4 + i];
@@ -382,34 +447,8 @@ pair_step_kernel(PairState st, const double* __restrict__ G3, double* __restrict
         s_lucky = sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2] + R[3] * R[3]) < 1e-8;   // lanczos_krylov.m:91
     }
     __syncthreads();
-    // ---- projected matrices: Gm = H(1:2j, 1:2j) symmetrised, tGm = Gm + Cm    (trace_fun_update.m:72-81)
-    const int nn = 2 * j, lda = nn | 1;
-    double* G = gscratch ? gscratch + (int64_t)h * gscratch_stride : dyn;
-    double* tG = G + nn * lda;
-    double* d1 = tG + nn * lda;
-    double* d2 = d1 + nn;
-    for (int e = threadIdx.x; e < nn * nn; e += JAC_THREADS) {
-        int r = e % nn, c = e / nn;
-        int br = r >> 1, bc = c >> 1, ir = r & 1, ic = c & 1;
-        // H(r, c): block (br, bc); column block bc is step bc+1
-        auto Hval = [&](int rr, int cc, int irr, int icc) -> double {
-            if (rr == cc) return Hd[cc * 4 + irr * 2 + icc];
-            if (rr == cc - 1) return Hs[cc * 4 + irr * 2 + icc];
-            if (rr == cc + 1) return Hr[cc * 4 + irr * 2 + icc];
-            return 0.0;
-        };
-        double v = 0.5 * (Hval(br, bc, ir, ic) + Hval(bc, br, ic, ir));
-        G[r + c * lda] = v;
-        // Cm = B in the leading 2x2 block (V1 = U, so V1'U = I): B = b_off * [0 1; 1 0]
-        double cm = (r < 2 && c < 2 && r != c) ? st.b_off : 0.0;
-        tG[r + c * lda] = v + cm;
-    }
-    __syncthreads();
-    block_jacobi(tG, nn, lda, nullptr, 0, &sh);
-    block_sorted_diag(tG, nn, lda, d1);
-    block_jacobi(G, nn, lda, nullptr, 0, &sh);
-    block_sorted_diag(G, nn, lda, d2);
-    const double Xm = block_trace_formula(st.fun, d1, d2, nn, sh.red);
+    double* work = gscratch ? gscratch + (int64_t)h * gscratch_stride : dyn;
+    const double Xm = pair_projected_trace<JAC_THREADS>(Hd, Hs, Hr, j, st.b_off, st.fun, work, &sh, st.eig_jacobi != 0);
     if (threadIdx.x == 0) {
         bool done = false;
         double* Xs = st.Xstop + h * 2;
@@ -477,6 +516,7 @@ inline void pairs_run(kr_ctx* ctx, const kr_matrix* M, const int64_t* Ei, const 
     istate.zero();
     PairState st;
     st.nslots = ns; st.it = it; st.fun = fun; st.tol = tol; st.b_off = b_off;
+    st.eig_jacobi = pair_eig_jacobi();
     double* d = dstate.p;
     st.Tp = d; d += ns * 4;
     st.Tc = d; d += ns * 4;

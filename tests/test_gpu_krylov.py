@@ -122,10 +122,13 @@ def test_trace_fun_update_edges_slot_reseeding(kr, O, graphs, monkeypatch):
     tol = 1e-6 * np.exp(nrm)
     c = O.compute_centrality(A, "eig")
     E = np.concatenate([O.find_top_edges(A, c, 48, "min"), O.find_top_missing_edges(A, c, 48, "min")])
+    # default dispatch on this graph (CSR L2-resident): the single-launch path of pairs_small.cuh, one persistent
+    # CTA per candidate.  KR_PAIR_SLOTS forces the batched slot pipeline of pairs.cuh.
+    small = [kr.trace_fun_update_edges(A, E[:48], -1.0, tol, 100, "exp"),
+             kr.trace_fun_update_edges(A, E[48:], 1.0, tol, 100, "exp")]
     ref = None
-    for slots in ("", "8", "24"):
-        if slots:
-            monkeypatch.setenv("KR_PAIR_SLOTS", slots)
+    for slots in ("8", "24", "4096"):
+        monkeypatch.setenv("KR_PAIR_SLOTS", slots)
         res = [kr.trace_fun_update_edges(A, E[:48], -1.0, tol, 100, "exp"),
                kr.trace_fun_update_edges(A, E[48:], 1.0, tol, 100, "exp")]
         if ref is None:
@@ -133,6 +136,12 @@ def test_trace_fun_update_edges_slot_reseeding(kr, O, graphs, monkeypatch):
         for (x, it, lk), (x0, it0, lk0) in zip(res, ref):
             assert np.array_equal(it, it0) and np.array_equal(lk, lk0)
             assert np.array_equal(x, x0), np.abs(x - x0).max()      # slot placement does not change the arithmetic
+    monkeypatch.delenv("KR_PAIR_SLOTS")
+    for (x, it, lk), (x0, it0, lk0) in zip(small, ref):            # same arithmetic, other summation order
+        assert np.array_equal(it, it0) and np.array_equal(lk, lk0)
+        assert np.all(np.abs(x - x0) <= RTOL * np.abs(x0)), np.abs(x / x0 - 1).max()
+    again = kr.trace_fun_update_edges(A, E[:48], -1.0, tol, 100, "exp")
+    assert np.array_equal(again[0], small[0][0])                   # bit-reproducible run to run
     for h in range(0, 96, 5):
         sign = -1.0 if h < 48 else 1.0
         U, B = edge_UB(n, int(E[h, 0]), int(E[h, 1]), sign)
