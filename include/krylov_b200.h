@@ -67,6 +67,17 @@ int  kr_matrix_info(const kr_matrix* A, int64_t* n, int64_t* nnz, int* symmetric
  * (functions/krylov_miobi.m:127-135). */
 int  kr_matrix_set_edges(kr_matrix* A, int64_t count, const int64_t* i, const int64_t* j, const double* v);
 
+/* Multi-GPU inside ONE process (A replicated - it fits 180 GB many times over - and the independent
+ * units of the path split across GPUs with one exchange of scalars).  Puts a replica of A, with a context and stream
+ * of its own, on each listed device (ndev <= 0 or devices == NULL: the first |ndev| / all visible devices).
+ * Afterwards kr_trace_fun_update_edges(_ex) splits its candidate edges and kr_slq_trace(_sign) its probe columns
+ * contiguously across the replicas, one host thread per GPU, results gathered in the caller's buffers
+ * (functions/krylov_miobi.m:76-124: candidate loop + arg-min over all scores; trace partials summed in a fixed
+ * order); kr_matrix_set_edges edits every replica.  Environment KR_GPUS=N makes kr_matrix_create do this itself, so
+ * that callers that know nothing about devices - the MATLAB wrappers, Tests/<name>.m unchanged - use N GPUs. */
+int  kr_matrix_replicate(kr_matrix* A, int ndev, const int* devices);
+int  kr_matrix_replicas(const kr_matrix* A);          /* 1 + number of replicas */
+
 int  kr_dense_create(kr_ctx* ctx, int64_t n, int64_t k, kr_dense** out);
 void kr_dense_destroy(kr_dense* d);
 int  kr_dense_upload(kr_dense* d, const double* host, int64_t ld);     /* col-major host -> device */

@@ -37,6 +37,8 @@ PROTOTYPES = {
     "kr_dense_download": [VP, VP, c_i64],
     "kr_dense_fill_rademacher": [VP, C.c_uint64, c_i64],
     "kr_spmm": [VP, VP, c_i64, VP, c_i64, VP, c_i64],
+    "kr_matrix_replicate": [VP, C.c_int, VP],
+    "kr_matrix_replicas": [VP],
     "kr_spmm_dev": [VP, VP, VP, VP],
     "kr_krylov_start": [VP, VP, C.c_int, c_i64, VP, c_i64, C.POINTER(VP), c_intp],
     "kr_krylov_extend": [VP, c_intp],

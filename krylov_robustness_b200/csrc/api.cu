@@ -1,6 +1,7 @@
 // api.cu - extern "C" entry points of libkrylov_b200.so (see include/krylov_b200.h).
 // Single translation unit: all kernels live in the .cuh files included below.
 #include <memory>
+#include <thread>
 #include "common.cuh"
 #include "csr.cuh"
 #include "spmm.cuh"
@@ -143,14 +144,83 @@ int kr_matrix_create(kr_ctx* ctx, int64_t n, int64_t nnz, const int64_t* row_ptr
         if (bad) fail(KR_ERR_ARG, "kr_matrix_create: column index out of range (The matrix A should be square)");
         analyse_and_upload(M.get());
         *out = M.release();
+        // KR_GPUS=N: every matrix is replicated on N GPUs of this process, so callers that know nothing about devices
+        // (the MATLAB wrappers: Tests/*.m unchanged) shard their candidate edges / probe columns across them
+        if (const char* e = getenv("KR_GPUS")) {
+            const int want = atoi(e);
+            if (want > 1 && kr_matrix_replicate(*out, want, nullptr) != 0) {
+                const std::string m = kr_last_error();
+                kr_matrix_destroy(*out);
+                *out = nullptr;
+                fail(KR_ERR_CUDA, "KR_GPUS=%d: %s", want, m.c_str());
+            }
+        }
     });
 }
 
 void kr_matrix_destroy(kr_matrix* A) {
     if (!A) return;
+    for (kr_matrix* P : A->peers) {              // replicas own their context
+        kr_ctx* pc = P->ctx;
+        cudaSetDevice(pc->device);
+        delete P;
+        kr_ctx_destroy(pc);
+    }
+    A->peers.clear();
     cudaSetDevice(A->ctx->device);
     delete A;
 }
+
+int kr_matrix_replicate(kr_matrix* A, int ndev, const int* devices) {
+    return guarded([&] {
+        if (!A || A->is_peer) fail(KR_ERR_ARG, "kr_matrix_replicate: null matrix or a replica");
+        if (!A->peers.empty()) fail(KR_ERR_ARG, "kr_matrix_replicate: the matrix already has replicas");
+        int count = 0;
+        KR_CUDA(cudaGetDeviceCount(&count));
+        std::vector<int> devs;
+        if (ndev <= 0 || !devices) {
+            const int want = ndev <= 0 ? count : std::min(ndev, count);
+            for (int d = 0; d < count && (int)devs.size() < want - 1; ++d)
+                if (d != A->ctx->device) devs.push_back(d);
+        } else {
+            for (int k = 0; k < ndev; ++k) {
+                if (devices[k] < 0 || devices[k] >= count) fail(KR_ERR_ARG, "kr_matrix_replicate: device %d out of range", devices[k]);
+                if (devices[k] != A->ctx->device) devs.push_back(devices[k]);
+            }
+        }
+        materialize(A);                              // replicas start from the current matrix
+        const CsrHost& H = A->host;
+        std::vector<int> status(devs.size(), 0);
+        std::vector<std::string> msg(devs.size());
+        std::vector<kr_matrix*> made(devs.size(), nullptr);
+        std::vector<std::thread> th;
+        for (size_t k = 0; k < devs.size(); ++k)
+            th.emplace_back([&, k] {
+                status[k] = guarded([&] {
+                    kr_ctx* pc = nullptr;
+                    if (kr_ctx_create(devs[k], &pc) != 0) fail(KR_ERR_CUDA, "%s", kr_last_error());
+                    std::unique_ptr<kr_matrix> M(new kr_matrix());
+                    M->ctx = pc;
+                    M->host = H;
+                    M->is_peer = true;
+                    try { analyse_and_upload(M.get()); } catch (...) { M.reset(); kr_ctx_destroy(pc); throw; }
+                    made[k] = M.release();
+                });
+                if (status[k]) msg[k] = kr_last_error();
+            });
+        for (auto& t : th) t.join();
+        for (size_t k = 0; k < devs.size(); ++k)
+            if (status[k]) {
+                for (kr_matrix* P : made)
+                    if (P) { kr_ctx* pc = P->ctx; cudaSetDevice(pc->device); delete P; kr_ctx_destroy(pc); }
+                fail(status[k], "%s", msg[k].c_str());
+            }
+        A->peers = made;
+        KR_CUDA(cudaSetDevice(A->ctx->device));
+    });
+}
+
+int kr_matrix_replicas(const kr_matrix* A) { return A ? 1 + (int)A->peers.size() : 0; }
 
 int kr_matrix_info(const kr_matrix* A, int64_t* n, int64_t* nnz, int* symmetric, int* pattern_only,
                    int* nonnegative) {
@@ -184,6 +254,9 @@ int kr_matrix_set_edges(kr_matrix* A, int64_t count, const int64_t* ii, const in
         // round.  Unsymmetric matrices (a transposed copy exists) and very long edit lists take the rebuild.
         if (!A->symmetric || A->pending.size() > KR_MAX_PENDING || getenv("KR_SET_EDGES_REBUILD")) flush_pending(A);
         else upload_pending(A);
+        for (kr_matrix* P : A->peers)                // the same edit on every replica (a few hundred bytes each)
+            if (kr_matrix_set_edges(P, count, ii, jj, v) != 0) fail(KR_ERR_CUDA, "replica on device %d: %s", P->ctx->device, kr_last_error());
+        KR_CUDA(cudaSetDevice(A->ctx->device));
     });
 }
 
@@ -379,16 +452,48 @@ static int slq_trace_host(kr_ctx* ctx, const kr_matrix* A, int64_t k, const T* Z
     });
 }
 
+// Probe columns split contiguously across the replicas of A (A replicated, columns sharded), one host
+// thread per GPU; the exchange step is the sum of the per-GPU partial traces, done on the host.
+template <class T>
+static int slq_trace_sharded(kr_ctx* ctx, const kr_matrix* A, int64_t k, const T* Z, int64_t ldz, int64_t m, int fun,
+                             double* tr, double* vals, double* alpha, double* beta) {
+    const int R = 1 + (int)A->peers.size();
+    if (R == 1 || k < 2 * R || !Z) return slq_trace_host<T>(ctx, A, k, Z, ldz, m, fun, tr, vals, alpha, beta);
+    std::vector<int> status(R, 0);
+    std::vector<std::string> msg(R);
+    std::vector<double> part(R, 0.0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; ++r)
+        th.emplace_back([&, r] {
+            const int64_t lo = k * r / R, hi = k * (r + 1) / R;
+            const kr_matrix* Ar = r == 0 ? A : A->peers[(size_t)r - 1];
+            status[r] = slq_trace_host<T>(r == 0 ? ctx : Ar->ctx, Ar, hi - lo, Z + lo * ldz, ldz, m, fun, &part[r],
+                                          vals ? vals + lo : nullptr, alpha ? alpha + lo * m : nullptr,
+                                          beta ? beta + lo * m : nullptr);
+            if (status[r]) msg[r] = kr_last_error();
+        });
+    for (auto& t : th) t.join();
+    cudaSetDevice(ctx->device);
+    for (int r = 0; r < R; ++r)
+        if (status[r]) { tls_error() = msg[r]; return status[r]; }
+    double s = 0.0;
+    for (int r = 0; r < R; ++r) s += part[r] * (double)(k * (r + 1) / R - k * r / R);     // fixed order
+    if (tr) *tr = s / (double)k;
+    return KR_OK;
+}
+
 extern "C" {
 
 int kr_slq_trace(kr_ctx* ctx, const kr_matrix* A, int64_t k, const double* Z, int64_t ldz, int64_t m, int fun,
                  double* tr, double* vals, double* alpha, double* beta) {
-    return slq_trace_host<double>(ctx, A, k, Z, ldz, m, fun, tr, vals, alpha, beta);
+    if (!ctx || !A) { tls_error() = "kr_slq_trace: null argument"; return KR_ERR_ARG; }
+    return slq_trace_sharded<double>(ctx, A, k, Z, ldz, m, fun, tr, vals, alpha, beta);
 }
 
 int kr_slq_trace_sign(kr_ctx* ctx, const kr_matrix* A, int64_t k, const signed char* Z, int64_t ldz, int64_t m, int fun,
                       double* tr, double* vals, double* alpha, double* beta) {
-    return slq_trace_host<signed char>(ctx, A, k, Z, ldz, m, fun, tr, vals, alpha, beta);
+    if (!ctx || !A) { tls_error() = "kr_slq_trace: null argument"; return KR_ERR_ARG; }
+    return slq_trace_sharded<signed char>(ctx, A, k, Z, ldz, m, fun, tr, vals, alpha, beta);
 }
 
 int kr_theta(double theta[100]) {

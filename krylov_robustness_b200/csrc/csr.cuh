@@ -262,6 +262,9 @@ struct kr_matrix {
     bool nonnegative = true;
     double trace = 0.0;
     double norm1 = 0.0;        // max column abs sum
+    // replicas of this matrix on other GPUs of the same process (kr_matrix_replicate): each owns its context
+    std::vector<kr_matrix*> peers;
+    bool is_peer = false;
     const kr::CsrDev& T() const { return symmetric ? dev : devT; }
 };
 

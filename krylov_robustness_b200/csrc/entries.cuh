@@ -297,11 +297,9 @@ inline EntriesResult entries_run(kr_ctx* ctx, const kr_matrix* M, const std::vec
     int* nactive = istate.p + 2 * R;
     int nact = R;
     KR_CUDA(cudaMemcpyAsync(nactive, &nact, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};              // per device: the attribute lives in the device's primary context
+    if (first_use_on_device(attr_set, ctx->device))
         KR_CUDA(cudaFuncSetAttribute(entries_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_LIMIT));
-        attr_set = true;
-    }
     EntriesResult out;
     int j = 0;
     for (j = 0; j < it; ++j) {                 // step j+1 of the reference

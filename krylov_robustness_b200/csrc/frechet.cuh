@@ -187,11 +187,9 @@ inline HessianResult frechet_hessian_run(kr_ctx* ctx, const kr_matrix* M, int64_
     int* nactive = istate.p + 2 * m;
     int nact = (int)m;
     KR_CUDA(cudaMemcpyAsync(nactive, &nact, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};              // per device: the attribute lives in the device's primary context
+    if (first_use_on_device(attr_set, ctx->device))
         KR_CUDA(cudaFuncSetAttribute(frechet_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_LIMIT));
-        attr_set = true;
-    }
     HessianResult out;
     int j = 0;
     for (j = 0; j < it; ++j) {

@@ -136,6 +136,20 @@ class Matrix:
         v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), i.shape))
         check(self.ctx.lib.kr_matrix_set_edges(self.h, i.size, _ptr(i), _ptr(j), _ptr(v)))
 
+    def replicate(self, devices=None):
+        """Multi-GPU in one process (kr_matrix_replicate): a replica of A on every listed device (None: all visible
+        ones).  Afterwards trace_fun_update_edges splits its candidates and slq_trace (host probes) its columns across
+        the replicas; set_edges edits all of them.  Returns the number of GPUs holding A."""
+        if devices is None:
+            check(self.ctx.lib.kr_matrix_replicate(self.h, 0, None))
+        else:
+            d = np.ascontiguousarray(devices, dtype=np.int32)
+            check(self.ctx.lib.kr_matrix_replicate(self.h, int(d.size), _ptr(d)))
+        return self.replicas()
+
+    def replicas(self):
+        return int(self.ctx.lib.kr_matrix_replicas(self.h))
+
     def multiply(self, alpha, beta, w):
         """The reference's operator-struct plug-in point: A.multiply(1.0, 0.0, w)
         (functions/lanczos_krylov.m:78-79)."""
