@@ -483,11 +483,16 @@ def _issymmetric(A):
 
 def select_candidate(vals, miobi):
     """First-wins strict comparison of functions/krylov_miobi.m:112-124."""
-    best, bestval = -1, (np.inf if miobi == "break" else -np.inf)
-    for h, v in enumerate(vals):
-        if (miobi == "break" and v < bestval) or (miobi == "make" and v > bestval):
-            best, bestval = h, v
-    return best, bestval
+    vals = np.asarray(vals, dtype=np.float64)
+    # a strict comparison against +-inf skips NaN and infinities of the wrong sign; argmin / argmax return the FIRST
+    # extremum, i.e. the reference's first-wins rule
+    key = np.where(np.isnan(vals), np.inf, vals) if miobi == "break" else np.where(np.isnan(vals), -np.inf, vals)
+    if key.size == 0:
+        return -1, (np.inf if miobi == "break" else -np.inf)
+    best = int(np.argmin(key)) if miobi == "break" else int(np.argmax(key))
+    if not (key[best] < np.inf if miobi == "break" else key[best] > -np.inf):
+        return -1, (np.inf if miobi == "break" else -np.inf)
+    return best, float(vals[best])
 
 
 def krylov_miobi(A, k, E=None, tol=1e-12, it=None, poles=np.inf, debug=0, miobi="break", rescale=1.0, scorer=None):
