@@ -259,7 +259,7 @@ struct kr_krylov {
     kr::DevBuf<int> lucky_dev;
     kr::DevBuf<const double*> hcol_ptr, hsub_ptr;           // device copies of the block pointers (grown as needed)
     std::vector<const double*> hcol_host, hsub_host;        // their host staging (must outlive the async copies)
-    kr::HqrWork qr;
+    kr::ThinQrWork qr;
     kr::DevBuf<double> scratch, h1;
     bool lucky = false;                                     // valid after sync_lucky()
     int64_t vcols() const { return (int64_t)V.size() * bs; }
@@ -329,9 +329,9 @@ inline void krylov_step(kr_krylov* st) {
     ts_update(ctx, Vl, Wl, n, st->h1.p);
     KR_LAUNCH(ctx, add_inplace_kernel, eg, 256, 0, h, st->h1.p, (int64_t)hsz);
     // [w, R] = qr(w, 0)
-    hqr_thin(ctx, Wl, n, bs, st->qr);
+    thin_qr(ctx, *W, bs, st->qr);
     if (!st->lucky_dev.p) st->lucky_dev.reset(ctx, 1);
-    KR_LAUNCH(ctx, hsub_lucky_kernel, 1, 256, 0, st->qr.st.R, bs, bpad, st->hsub.back().p, (int)st->arnoldi, st->lucky_dev.p);
+    KR_LAUNCH(ctx, hsub_lucky_kernel, 1, 256, 0, st->qr.hqr.st.R, bs, bpad, st->hsub.back().p, (int)st->arnoldi, st->lucky_dev.p);
     if (st->arnoldi) {
         // third reorthogonalisation (arnoldi_krylov.m:104-106): hh = V'w; w -= V hh; H(1:end-bs, last) += hh R
         ts_gram(ctx, Vl, Wl, n, st->h1.p, st->scratch);
@@ -365,7 +365,7 @@ inline std::unique_ptr<kr_krylov> krylov_start(kr_ctx* ctx, const kr_matrix* A, 
     st->ctx = ctx; st->A = A; st->arnoldi = arnoldi; st->n = n; st->bs = bs;
     st->bp = b->panels;
     st->bpad = b->panels * PW;
-    hqr_thin(ctx, list_of(*b), n, (int)bs, st->qr);
+    thin_qr(ctx, *b, (int)bs, st->qr);
     st->V.push_back(std::move(b));
     krylov_step(st.get());
     return st;

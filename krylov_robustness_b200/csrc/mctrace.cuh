@@ -18,7 +18,7 @@ inline McTraceResult mc_trace_dev(kr_ctx* ctx, const kr_matrix* M, int op, doubl
     std::vector<std::unique_ptr<PanelBuf>> Qs;                 // deflation bases Q_1..Q_i (panel-major, one panel each)
     const int mp = PW;                                         // padded width of a 10-column block
     DevBuf<double> small(ctx, (size_t)mp * mp), scratch;
-    HqrWork qr;
+    ThinQrWork qr;
 
     auto project = [&](const PanelBuf& Q, PanelBuf& X) {       // X -= Q (Q' X)      (:47)
         const PanelList Ql = list_of(Q), Xl = list_of(X);
@@ -58,7 +58,7 @@ inline McTraceResult mc_trace_dev(kr_ctx* ctx, const kr_matrix* M, int op, doubl
         upload_cm_block(ctx, probes + (size_t)(2 * (it - 1) + 1) * n * m, n, G);
         const int level = (int)Qs.size();
         apply(level, S, *Q);                                   // Afun(S)
-        hqr_thin(ctx, list_of(*Q), n, m, qr);                  // [Q,~] = qr(Afun(S),0)   (:45)
+        thin_qr(ctx, *Q, m, qr);                  // [Q,~] = qr(Afun(S),0)   (:45)
         PanelBuf AQ(ctx, n, m);
         apply(level, *Q, AQ);
         tr += trace_of(*Q, AQ);                                // :46

@@ -155,8 +155,13 @@ inline void ts_gram(kr_ctx* ctx, const PanelList& V, const PanelList& W, int64_t
 constexpr int TSU_HS = TSG_WP * PW + 4;
 constexpr size_t TSU_SMEM = (size_t)(TSG_VP * PW * TSU_HS + TSG_ROWS * TSG_VS) * sizeof(double);
 
+// OVERWRITE: W = V h instead (the right-multiplication of CholQR, V and W must be DIFFERENT blocks and V at most 128
+// columns wide so that there is a single V group); `skip` (may be null): do nothing if *skip != 0.
+template <bool OVERWRITE>
 __global__ void __launch_bounds__(256)
-ts_update_kernel(PanelList V, PanelList Wl, int64_t n, int rows_per_cta, const double* __restrict__ h) {
+ts_update_kernel(PanelList V, PanelList Wl, int64_t n, int rows_per_cta, const double* __restrict__ h,
+                 const int* __restrict__ skip) {
+    if (skip && *skip) return;
     extern __shared__ __align__(16) double ts_smem[];
     double* hs = ts_smem;                                   // [128][TSU_HS]: -h(group rows, this CTA's 64 columns)
     double* vs = ts_smem + TSG_VP * PW * TSU_HS;            // [32][TSG_VS]
@@ -174,7 +179,7 @@ ts_update_kernel(PanelList V, PanelList Wl, int64_t n, int rows_per_cta, const d
         for (int e = threadIdx.x; e < TSG_VP * PW * TSG_WP * PW; e += 256) {
             const int k = e % (TSG_VP * PW), c = e / (TSG_VP * PW);
             double v = 0.0;
-            if (k < nvp * PW && c < nwp * PW) v = -h[(vg * PW + k) + (int64_t)(wp0 * PW + c) * ldh];
+            if (k < nvp * PW && c < nwp * PW) v = (OVERWRITE ? 1.0 : -1.0) * h[(vg * PW + k) + (int64_t)(wp0 * PW + c) * ldh];
             hs[k * TSU_HS + c] = v;
         }
         for (int64_t row0 = r0; row0 < r1; row0 += TSG_ROWS) {
@@ -193,7 +198,7 @@ ts_update_kernel(PanelList V, PanelList Wl, int64_t n, int rows_per_cta, const d
             for (int t = 0; t < 4; ++t) {
                 const int col = ncol + t * 8 + 2 * kk;                 // column inside the CTA's 64
                 c0[t] = c1[t] = 0.0;
-                if (row < r1 && col < nwp * PW) {
+                if (!OVERWRITE && row < r1 && col < nwp * PW) {
                     const double2 w = *reinterpret_cast<const double2*>(Wl.p[wp0 + col / PW] + row * PW + col % PW);
                     c0[t] = w.x; c1[t] = w.y;
                 }
@@ -221,10 +226,22 @@ inline void ts_update(kr_ctx* ctx, const PanelList& V, const PanelList& W, int64
     if (V.count == 0 || W.count == 0) return;
     static bool attr_set[64] = {};
     if (first_use_on_device(attr_set, ctx->device))
-        KR_CUDA(cudaFuncSetAttribute(ts_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSU_SMEM));
+        KR_CUDA(cudaFuncSetAttribute(ts_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSU_SMEM));
     const int rows = ts_rows_per_cta(ctx, n);
     dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(n, rows)), (unsigned)ceil_div(W.count, TSG_WP));
-    KR_LAUNCH(ctx, ts_update_kernel, grid, 256, TSU_SMEM, V, W, n, rows, h);
+    KR_LAUNCH(ctx, ts_update_kernel<false>, grid, 256, TSU_SMEM, V, W, n, rows, h, (const int*)nullptr);
+}
+
+// W = V m   (m: column-major (V.count*16) x (W.count*16), device); V and W distinct, V.count <= 8
+inline void ts_rightmul(kr_ctx* ctx, const PanelList& V, const PanelList& W, int64_t n, const double* m, const int* skip) {
+    if (V.count == 0 || W.count == 0) return;
+    if (V.count > TSG_VP) fail(KR_ERR_UNSUPPORTED, "ts_rightmul: block wider than %d columns", TSG_VP * PW);
+    static bool attr_set[64] = {};
+    if (first_use_on_device(attr_set, ctx->device))
+        KR_CUDA(cudaFuncSetAttribute(ts_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSU_SMEM));
+    const int rows = ts_rows_per_cta(ctx, n);
+    dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(n, rows)), (unsigned)ceil_div(W.count, TSG_WP));
+    KR_LAUNCH(ctx, ts_update_kernel<true>, grid, 256, TSU_SMEM, V, W, n, rows, m, skip);
 }
 
 // ------------------------------------------------------------------------------------ Householder QR
@@ -451,6 +468,170 @@ inline void hqr_thin(kr_ctx* ctx, const PanelList& W, int64_t n, int bs, HqrWork
     KR_LAUNCH(ctx, hqr_clear_kernel, 8, 256, 0, work.st.partial, 2 * (size_t)work.nctas * HQR_MAXB);
     for (int k = bs - 1; k >= 0; --k)
         KR_LAUNCH(ctx, hqr_formq_pass_kernel, work.nctas, HQR_THREADS, 0, W, n, bs, k, work.st, work.nctas);
+}
+
+// ------------------------------------------------------------------------------------ CholQR2 + Householder signs
+// The passes of hqr_thin above cost 2*bs + 1 launches per factorisation: on the reference's graphs (launch-bound)
+// and on large ones (latency-bound row loops) they were 97 % of a block Krylov step (profiles/
+// r02l_launches_arnoldi_bs64.csv).  For a block of full numerical rank the SAME factors come from two rounds of
+// Cholesky QR (Gram on the tensor cores, bs x bs Cholesky in one CTA, right-multiplication on the tensor cores):
+//   W = Q+ R+ with diag(R+) > 0 is unique, and LAPACK's Householder factors are Q = Q+ S, R = S R+ with the signs
+//   s_k = -sgn(alpha_k) of dlarfg, which the elimination of "Reconstructing Householder vectors from tall-skinny
+//   QR" (Ballard et al., 2014) recovers from the TOP bs x bs block of Q+ alone (checked against LAPACK on 300
+//   random and badly scaled blocks: factors equal to 1e-12, all signs equal).
+// A block whose Cholesky pivot falls below 1e-10 of its diagonal (condition number beyond ~1e5), an exactly zero
+// column included, is left untouched and goes through hqr_thin: the reference's dgeqr2/dorg2r semantics for rank
+// deficient blocks (tau = 0, coordinate-vector completion) are kept to the letter.
+constexpr int CQ_THREADS = 256;
+constexpr int CQ_MAXB = 80;          // three bs x (bs+1) matrices in shared memory: 155 KB at 80; wider blocks take hqr_thin
+
+// pass 1: G -> R1 (to Rkeep), R1^{-1} (to Minv);  pass 2: G -> R2, signs from top(S) R2^{-1}, Minv = R2^{-1} D,
+// Rout = D R2 R1.  All matrices column-major with leading dimension ld (>= bs; padding kept zero).  flag: set to 1
+// on breakdown (never cleared here).  Single CTA; dynamic shared memory: 3 * bs * (bs + 1) doubles.
+__global__ void __launch_bounds__(CQ_THREADS)
+cholqr_factor_kernel(const double* __restrict__ G, int bs, int ld, int pass, double* __restrict__ Rkeep,
+                     double* __restrict__ Minv, double* __restrict__ Rout, PanelList S, int* __restrict__ flag) {
+    extern __shared__ double cq[];
+    __shared__ double s_sign[HQR_MAXB];
+    const int tid = threadIdx.x, ls = bs + 1;
+    double* R = cq;                    // upper triangular factor
+    double* Ri = R + bs * ls;          // its inverse
+    double* T = Ri + bs * ls;          // scratch: top(S) * Ri, or R2 * R1
+    if (*flag) return;
+    for (int e = tid; e < bs * bs; e += CQ_THREADS) {
+        const int i = e % bs, j = e / bs;
+        R[i + j * ls] = i <= j ? G[i + (size_t)j * ld] : 0.0;
+        Ri[i + j * ls] = 0.0;
+    }
+    __syncthreads();
+    // right-looking Cholesky, upper: row k of R, then the trailing update
+    for (int k = 0; k < bs; ++k) {
+        const double gkk = G[k + (size_t)k * ld];
+        const double d = R[k + k * ls];
+        if (!(d > 1e-10 * gkk) || !(gkk > 0.0)) {      // uniform: every thread reads the same values
+            if (tid == 0) *flag = 1;
+            return;
+        }
+        const double rkk = sqrt(d);
+        __syncthreads();
+        for (int j = k + tid; j < bs; j += CQ_THREADS) R[k + j * ls] = j == k ? rkk : R[k + j * ls] / rkk;
+        __syncthreads();
+        for (int e = tid; e < (bs - k - 1) * (bs - k - 1); e += CQ_THREADS) {
+            const int i = k + 1 + e % (bs - k - 1), j = k + 1 + e / (bs - k - 1);
+            if (i <= j) R[i + j * ls] -= R[k + i * ls] * R[k + j * ls];
+        }
+        __syncthreads();
+    }
+    // inverse of the upper triangular R, column by column (thread per column, back substitution)
+    for (int j = tid; j < bs; j += CQ_THREADS) {
+        for (int i = j; i >= 0; --i) {
+            double acc = i == j ? 1.0 : 0.0;
+            for (int l = i + 1; l <= j; ++l) acc -= R[i + l * ls] * Ri[l + j * ls];
+            Ri[i + j * ls] = acc / R[i + i * ls];
+        }
+    }
+    __syncthreads();
+    if (pass == 1) {
+        for (int e = tid; e < bs * bs; e += CQ_THREADS) {
+            const int i = e % bs, j = e / bs;
+            Rkeep[i + (size_t)j * ld] = R[i + j * ls];
+            Minv[i + (size_t)j * ld] = Ri[i + j * ls];
+        }
+        return;
+    }
+    // ---- pass 2: signs of LAPACK's Householder factors from the top block of Q+ = S * Ri
+    for (int e = tid; e < bs * bs; e += CQ_THREADS) {
+        const int i = e % bs, j = e / bs;          // T(i, j) = sum_l S(i, l) Ri(l, j), l <= j
+        double acc = 0.0;
+        for (int l = 0; l <= j; ++l) acc += S.p[l / PW][(int64_t)i * PW + l % PW] * Ri[l + j * ls];
+        T[i + j * ls] = acc;
+    }
+    __syncthreads();
+    for (int k = 0; k < bs; ++k) {
+        if (tid == 0) {
+            const double t = T[k + k * ls];
+            const double sg = t >= 0.0 ? -1.0 : 1.0;   // s_k = -sgn(alpha_k), sgn(0) = +1 (copysign in dlarfg)
+            s_sign[k] = sg;
+            T[k + k * ls] = t - sg;
+        }
+        __syncthreads();
+        const double piv = T[k + k * ls];              // |piv| >= 1
+        for (int e = tid; e < (bs - k - 1) * (bs - k - 1); e += CQ_THREADS) {
+            const int i = k + 1 + e % (bs - k - 1), j = k + 1 + e / (bs - k - 1);
+            T[i + j * ls] -= (T[i + k * ls] / piv) * T[k + j * ls];
+        }
+        __syncthreads();
+    }
+    // Minv = Ri * D;  Rout = D * (R2 * R1)
+    for (int e = tid; e < bs * bs; e += CQ_THREADS) {
+        const int i = e % bs, j = e / bs;
+        Minv[i + (size_t)j * ld] = Ri[i + j * ls] * s_sign[j];
+        double acc = 0.0;
+        if (i <= j)
+            for (int l = i; l <= j; ++l) acc += R[i + l * ls] * Rkeep[l + (size_t)j * ld];
+        T[i + j * ls] = acc * s_sign[i];
+    }
+    __syncthreads();
+    for (int e = tid; e < bs * bs; e += CQ_THREADS) {
+        const int i = e % bs, j = e / bs;
+        Rout[i + (size_t)j * bs] = T[i + j * ls];      // HqrState::R is bs x bs, leading dimension bs
+    }
+}
+
+struct ThinQrWork {
+    HqrWork hqr;                       // the fall-back, and the owner of R (hqr.st.R: bs x bs column-major)
+    DevBuf<double> G, R1, Minv, gscratch;
+    DevBuf<int> flag;
+    std::unique_ptr<PanelBuf> S;       // the intermediate block of the two-round scheme
+    int64_t fallbacks = 0, calls = 0;
+};
+
+inline bool thin_qr_use_cholqr() {
+    static const bool v = [] { const char* e = getenv("KR_QR_HOUSEHOLDER"); return !(e && atoi(e) != 0); }();
+    return v;
+}
+
+// W (n x bs block given as one PanelBuf) <- Q of qr(W, 0) with LAPACK's sign conventions; work.hqr.st.R <- R.
+// Synchronises once (the breakdown flag decides between the two routes on the host).
+inline void thin_qr(kr_ctx* ctx, PanelBuf& Wb, int bs, ThinQrWork& work) {
+    const int64_t n = Wb.n;
+    PanelList W;
+    W.add(Wb);
+    work.calls += 1;
+    if (!thin_qr_use_cholqr() || n < bs || bs > CQ_MAXB) {
+        hqr_thin(ctx, W, n, bs, work.hqr);
+        return;
+    }
+    if (bs > HQR_MAXB) fail(KR_ERR_UNSUPPORTED, "thin QR: block width %d exceeds %d", bs, HQR_MAXB);
+    work.hqr.prepare(ctx, n, bs);
+    const int ld = Wb.panels * PW;
+    const size_t msz = (size_t)ld * ld;
+    if (work.G.count < msz) { work.G.reset(ctx, msz); work.R1.reset(ctx, msz); work.Minv.reset(ctx, msz); }
+    if (!work.flag.p) work.flag.reset(ctx, 1);
+    if (!work.S || work.S->n != n || work.S->cols != Wb.cols) work.S.reset(new PanelBuf(ctx, n, Wb.cols));
+    PanelList S;
+    S.add(*work.S);
+    static bool attr_set[64] = {};
+    const size_t smem = (size_t)3 * bs * (bs + 1) * sizeof(double);
+    if (first_use_on_device(attr_set, ctx->device))
+        KR_CUDA(cudaFuncSetAttribute(cholqr_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)3 * CQ_MAXB * (CQ_MAXB + 1) * sizeof(double))));
+    KR_CUDA(cudaMemsetAsync(work.flag.p, 0, sizeof(int), ctx->stream));
+    KR_CUDA(cudaMemsetAsync(work.Minv.p, 0, msz * sizeof(double), ctx->stream));
+    KR_CUDA(cudaMemsetAsync(work.R1.p, 0, msz * sizeof(double), ctx->stream));
+    ts_gram(ctx, W, W, n, work.G.p, work.gscratch);
+    KR_LAUNCH(ctx, cholqr_factor_kernel, 1, CQ_THREADS, smem, work.G.p, bs, ld, 1, work.R1.p, work.Minv.p, work.hqr.st.R, S, work.flag.p);
+    ts_rightmul(ctx, W, S, n, work.Minv.p, work.flag.p);
+    ts_gram(ctx, S, S, n, work.G.p, work.gscratch);
+    KR_LAUNCH(ctx, cholqr_factor_kernel, 1, CQ_THREADS, smem, work.G.p, bs, ld, 2, work.R1.p, work.Minv.p, work.hqr.st.R, S, work.flag.p);
+    ts_rightmul(ctx, S, W, n, work.Minv.p, work.flag.p);
+    int bad = 0;
+    KR_CUDA(cudaMemcpyAsync(&bad, work.flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad) {                          // rank deficient or ill conditioned: W is untouched
+        work.fallbacks += 1;
+        hqr_thin(ctx, W, n, bs, work.hqr);
+    }
 }
 
 }  // namespace kr
