@@ -418,6 +418,37 @@ def run_ours(args):
         if its.size:
             secondary["roofline_edges_per_sec_per_gpu"] = peak_gbs() * 1e9 / b_mv / (2.0 * float(its.mean()))
             secondary["frac_of_edge_roofline"] = secondary["value"] / world / secondary["roofline_edges_per_sec_per_gpu"]
+        # ---- the same greedy round with the node-basis screen (kr_greedy_round, csrc/nodepairs.cuh): shared per-node
+        # Krylov bases rule out the candidates that cannot win (values to 1e-9..1e-8, NOT the parity path); only the
+        # contenders take the exact path and the selection runs on exact values.  Each rank screens its own shard, one
+        # all-gather of (index, value) pairs, first-wins over the rank order.
+        if os.environ.get("KR_BENCH_SCREEN", "1") != "0":
+            def screened_round(Ecand):
+                lo_, hi_ = P.shard_bounds(Ecand.shape[0])
+                b, v, sc, mask, info = kr.greedy_round(M, Ecand[lo_:hi_], b_off, tol_e, 100, "exp", "make", screen=True)
+                mine = torch.tensor([float(lo_ + b) if b >= 0 else -1.0, v if b >= 0 else float("-inf"), float(info["exact"]),
+                                     float(info["nodes"])], dtype=torch.float64, device="cuda")
+                allr = [torch.zeros_like(mine) for _ in range(world)] if world > 1 else [mine]
+                if world > 1:
+                    dist.all_gather(allr, mine)
+                rows = torch.stack(allr).cpu().numpy()
+                best_i, best_v = -1, float("-inf")
+                for r in rows:                       # rank order = candidate order: strict > keeps the first
+                    if r[0] >= 0 and r[1] > best_v:
+                        best_i, best_v = int(r[0]), float(r[1])
+                return best_i, best_v, rows, sc, mask
+            screened_round(E[:4000 * world])
+            ms_scr, (bi, bv, rows, sc, mask) = timed(lambda: screened_round(E), 1)
+            ex_best = int(np.argmax(vals))
+            lo, hi = P.shard_bounds(E.shape[0])
+            dev = np.abs(sc - vals[lo:hi]) / np.abs(vals[lo:hi])
+            secondary["screened_round"] = {
+                "metric": "edges_scored_per_sec", "value": E.shape[0] / (ms_scr * 1e-3), "unit": "edge/s", "ms_per_round": ms_scr,
+                "same_edge_and_value_as_exact_round": bool(bi == ex_best and bv == float(vals[ex_best])),
+                "exactly_rescored_candidates": int(rows[:, 2].sum()), "distinct_nodes_rank0": int(rows[0, 3]),
+                "screen_max_rel_deviation_rank0": float(dev.max()), "speedup_vs_exact_round": ms_edges / ms_scr,
+                "note": "NOT the 1e-10 parity path for the discarded candidates: the screen's values deviate by up to ~1e-8 "
+                        "relative; the selected edge and its value are those of the exact round (checked here)"}
 
     for _ in range(1):
         step_e2e()

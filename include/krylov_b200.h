@@ -124,6 +124,18 @@ int  kr_trace_fun_update_edges(kr_ctx* ctx, const kr_matrix* A, int64_t nE, cons
 int  kr_trace_fun_update_edges_ex(kr_ctx* ctx, const kr_matrix* A, int64_t nE, const int64_t* E,
                                   double b_offdiag, double b_self, double tol, int64_t it, int fun,
                                   double* Xm, int64_t* iter, int* lucky);
+/* One round of the greedy loop, functions/krylov_miobi.m:76-124: score every candidate edge (as
+ * kr_trace_fun_update_edges_ex) and select arg-min (mode 0, 'break') / arg-max (mode 1, 'make') with the reference's
+ * strict first-wins comparison (:112-124).  best = 0-based index into E (-1: none), best_val = its value.
+ * screen != 0: when the candidates are dense in few nodes (find_top_missing_edges(...,'min'): 10^5 candidates on ~520
+ * nodes) shared per-node Krylov bases rule out the candidates that cannot win (csrc/nodepairs.cuh: values to
+ * 1e-9..1e-8 relative, NOT the 1e-10 parity path) and only the contenders - within 1e-6 relative of the approximate
+ * leader, plus everything the screen could not settle - are scored by the exact path; the selection runs on exact
+ * values, so best / best_val equal those of screen == 0.  scores (nE, may be NULL): exact values where exact[h] != 0,
+ * screen values elsewhere.  info (may be NULL): {exactly scored, screened, distinct nodes, basis levels}. */
+int  kr_greedy_round(kr_ctx* ctx, const kr_matrix* A, int64_t nE, const int64_t* E, double b_offdiag, double b_self,
+                     double tol, int64_t it, int fun, int mode, int screen, int64_t* best, double* best_val,
+                     double* scores, int* exact, int64_t* info);
 /* [Xm,iter,lucky,Um] = fun_update(A,U,B,fun,tol,it,debug)       functions/fun_update.m:1-137
  * want_basis stands in for nargout == 4 (:69,:77).  Xm is returned column-major with leading
  * dimension xm_dim; Um (n x xm_dim, or the Lanczos window) only if want_basis.  Call with

@@ -19,6 +19,7 @@
 #include "entries.cuh"
 #include "frechet.cuh"
 #include "mctrace.cuh"
+#include "nodepairs.cuh"
 
 using namespace kr;
 

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -90,6 +91,7 @@ struct kr_ctx {
     // size-bucketed free lists (bytes rounded up to a power of two >= 512)
     std::multimap<size_t, void*> pool;
     size_t pool_bytes = 0;
+    std::unordered_map<void*, size_t> live;   // actual size of every block handed out (a request may get a larger one)
     // result of the last kr_fun_update, kept on the device until fetched
     struct FunUpdateResult* last_fun_update = nullptr;
 
@@ -184,11 +186,16 @@ inline void* kr_ctx::alloc(size_t bytes) {
     // debugging aid (KR_POOL_POISON=1): every buffer handed out is filled with NaN bit patterns first, so a kernel
     // that reads memory it (or a predecessor) never wrote turns the result into NaN instead of a plausible number
     static const bool poison = getenv("KR_POOL_POISON") != nullptr;
-    auto it = pool.find(b);
-    if (it != pool.end()) {
+    // best fit: the smallest cached block that holds the request, as long as it wastes less than half of itself
+    // (an exact-size pool fills up with blocks of sizes that never come back: the candidate pipeline, the SLQ pass and
+    // the node bases of one bench run all use different multi-GB shapes)
+    auto it = pool.lower_bound(b);
+    if (it != pool.end() && it->first <= b + b / 2) {
         void* p = it->second;
+        const size_t actual = it->first;
         pool.erase(it);
-        pool_bytes -= b;
+        pool_bytes -= actual;
+        live[p] = actual;
         if (poison) cudaMemsetAsync(p, 0xFF, b, stream);
         return p;
     }
@@ -203,19 +210,33 @@ inline void* kr_ctx::alloc(size_t bytes) {
             kr::fail(KR_ERR_NOMEM, "device allocation of %zu bytes failed: %s", b, cudaGetErrorString(e));
         }
     }
+    live[p] = b;
     if (poison) cudaMemsetAsync(p, 0xFF, b, stream);
     return p;
 }
 
 inline void kr_ctx::release(void* p, size_t bytes) {
     size_t b = kr::bucket(bytes);
+    auto lv = live.find(p);
+    if (lv != live.end()) { b = lv->second; live.erase(lv); }
     // keep at most 96 GiB cached (a B200 has 180 GB; the candidate-pair path cycles three ~17 GB blocks per
-    // chunk and must not pay cudaFree + cudaMalloc for one of them on every chunk); larger one-off buffers go
-    // straight back to the driver.  alloc() trims the pool and retries when the driver runs out.
-    if (pool_bytes + b > (size_t(96) << 30)) {
+    // chunk and must not pay cudaFree + cudaMalloc for one of them on every chunk).  Over the cap the LARGEST cached
+    // blocks go back to the driver first - the block being released is the most recently used shape and the most
+    // likely to be asked for again.  alloc() trims the whole pool and retries when the driver runs out.
+    const size_t cap = size_t(96) << 30;
+    if (b > cap) {
         cudaStreamSynchronize(stream);
         cudaFree(p);
         return;
+    }
+    if (pool_bytes + b > cap) {
+        cudaStreamSynchronize(stream);
+        while (!pool.empty() && pool_bytes + b > cap) {
+            auto last = std::prev(pool.end());
+            cudaFree(last->second);
+            pool_bytes -= last->first;
+            pool.erase(last);
+        }
     }
     pool.emplace(b, p);
     pool_bytes += b;

@@ -21,7 +21,7 @@ __all__ = ["slq_trace", "lanczos_krylov", "arnoldi_krylov", "trace_fun_update", 
            "fun_update", "function_multiple_entries", "fun_and_grad_krylov_exp", "fun_and_grad_krylov_fun",
            "normest", "normAm", "select_taylor_degree", "expmv", "ExpmvHandle", "mc_trace", "trace_exp",
            "edge2low_rank", "compute_centrality", "find_top_edges", "find_top_missing_edges",
-           "select_candidate", "krylov_miobi", "greedy_krylov", "KrylovParams", "fun_and_grad_all_edges", "hessianfcn_exp", "hessianfcn_fun"]
+           "select_candidate", "greedy_round", "krylov_miobi", "greedy_krylov", "KrylovParams", "fun_and_grad_all_edges", "hessianfcn_exp", "hessianfcn_fun"]
 
 
 def _mat(A, ctx=None):
@@ -180,6 +180,32 @@ def trace_fun_update_edges(A, E, b_offdiag, tol=1e-12, it=None, fun="exp", b_sel
                                                  float(b_offdiag if b_self is None else b_self), float(tol), it,
                                                  fun_id(fun), _ptr(x), _ptr(k), _ptr(lucky)))
     return x, k, lucky.astype(bool)
+
+
+def greedy_round(A, E, b_offdiag, tol=1e-12, it=None, fun="exp", miobi="break", screen=True, b_self=None):
+    """One round of the greedy loop (functions/krylov_miobi.m:76-124): score the candidates E and select arg-min
+    ('break') / arg-max ('make') with the reference's strict first-wins rule - kr_greedy_round.  With ``screen`` the
+    shared node bases of csrc/nodepairs.cuh rule out the candidates that cannot win whenever E is dense in few nodes
+    (the find_top_missing_edges case) and only the contenders take the exact path: the returned edge and value are
+    those of the exact round either way.
+    Returns (best, bestval, scores, exact_mask, info): best = row of E (-1: none); scores are exact where
+    exact_mask is set and screen values (1e-9 .. 1e-8 relative) elsewhere; info = dict(exact, screened, nodes, levels)."""
+    if miobi not in ("break", "make"):
+        raise ValueError("KRYLOV_MIOBI:: not supported option for miobi")
+    M = _mat(A)
+    it = _default_it(M, it)
+    E = np.asfortranarray(np.atleast_2d(np.asarray(E)).astype(np.int64))
+    nE = E.shape[0]
+    scores = np.zeros(nE)
+    mask = np.zeros(nE, dtype=np.int32)
+    info = np.zeros(4, dtype=np.int64)
+    best, bestval = C.c_int64(), C.c_double()
+    check(M.ctx.lib.kr_greedy_round(M.ctx.h, M.h, nE, _ptr(E), float(b_offdiag),
+                                    float(b_offdiag if b_self is None else b_self), float(tol), it, fun_id(fun),
+                                    0 if miobi == "break" else 1, int(bool(screen)), C.byref(best), C.byref(bestval),
+                                    _ptr(scores), _ptr(mask), _ptr(info)))
+    return (int(best.value), float(bestval.value), scores, mask.astype(bool),
+            dict(exact=int(info[0]), screened=int(info[1]), nodes=int(info[2]), levels=int(info[3])))
 
 
 def fun_update(A, U, B, fun, tol=1e-12, it=None, debug=0, nargout=3):
@@ -495,10 +521,12 @@ def select_candidate(vals, miobi):
     return best, float(vals[best])
 
 
-def krylov_miobi(A, k, E=None, tol=1e-12, it=None, poles=np.inf, debug=0, miobi="break", rescale=1.0, scorer=None):
+def krylov_miobi(A, k, E=None, tol=1e-12, it=None, poles=np.inf, debug=0, miobi="break", rescale=1.0, scorer=None,
+                 screen=False):
     """[edges,rob,A_new] = krylov_miobi(A,k,E,tol,it,poles,debug,miobi,rescale)
     (functions/krylov_miobi.m:1-142).  The candidate loop (:76-99) is one batched device call;
-    ``scorer(M, E, b_offdiag, tol, it)`` may replace it (multi-GPU sharding, tests)."""
+    ``scorer(M, E, b_offdiag, tol, it)`` may replace it (multi-GPU sharding, tests); ``screen`` runs each round
+    through greedy_round (candidates that cannot win are ruled out by shared node bases, the winner is exact)."""
     if not _issymmetric(A):
         raise ValueError("KRYLOV_MIOBI:: Adjacency matrix should be symmetric")
     if miobi not in ("break", "make"):
@@ -520,9 +548,12 @@ def krylov_miobi(A, k, E=None, tol=1e-12, it=None, poles=np.inf, debug=0, miobi=
     for _ in range(min(k, E.shape[0])):
         if scorer is not None:
             vals = np.asarray(scorer(M, E, sign / rescale, tol, it))
+            best, bestval = select_candidate(vals, miobi)
+        elif screen:
+            best, bestval = greedy_round(M, E, sign / rescale, tol, it, "exp", miobi, True, b_self=sign)[:2]
         else:
             vals = trace_fun_update_edges(M, E, sign / rescale, tol, it, "exp", b_self=sign)[0]
-        best, bestval = select_candidate(vals, miobi)
+            best, bestval = select_candidate(vals, miobi)
         chosen = E[best].copy()
         E = np.delete(E, best, axis=0)
         newval = 0.0 if miobi == "break" else 1.0
@@ -538,7 +569,7 @@ def krylov_miobi(A, k, E=None, tol=1e-12, it=None, poles=np.inf, debug=0, miobi=
 
 
 def greedy_krylov(A, k, Q=0, centrality=None, order="mult", tol=1e-12, it=None, poles=np.inf, debug=0, miobi="break",
-                  rescale=1.0, scorer=None):
+                  rescale=1.0, scorer=None, screen=False):
     """[edges,rob_variation,A_new] = greedy_krylov(A,k,Q,centrality,order,tol,it,poles,debug,miobi,rescale)
     (functions/greedy_krylov.m:1-97).  A stays resident on the device across the k rounds; each round is
     one batched scoring call plus an in-place edge update."""
@@ -566,9 +597,12 @@ def greedy_krylov(A, k, Q=0, centrality=None, order="mult", tol=1e-12, it=None, 
         E = top_edges[:Q]
         if scorer is not None:
             vals = np.asarray(scorer(M, E, sign / rescale, tol, it))
+            best, bestval = select_candidate(vals, miobi)
+        elif screen:
+            best, bestval = greedy_round(M, E, sign / rescale, tol, it, "exp", miobi, True, b_self=sign)[:2]
         else:
             vals = trace_fun_update_edges(M, E, sign / rescale, tol, it, "exp", b_self=sign)[0]
-        best, bestval = select_candidate(vals, miobi)
+            best, bestval = select_candidate(vals, miobi)
         chosen = E[best].copy()
         M.set_edges([chosen[0]], [chosen[1]], newval)
         A[chosen[0] - 1, chosen[1] - 1] = newval
