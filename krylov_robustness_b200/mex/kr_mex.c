@@ -206,6 +206,23 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         if (nlhs > 1) { plhs[1] = mxCreateDoubleMatrix(nE, 1, mxREAL); for (i = 0; i < nE; ++i) mxGetPr(plhs[1])[i] = (double)it[i]; }
         if (nlhs > 2) { plhs[2] = mxCreateDoubleMatrix(nE, 1, mxREAL); for (i = 0; i < nE; ++i) mxGetPr(plhs[2])[i] = (double)lk[i]; }
         mxFree(E); mxFree(it); mxFree(lk);
+    } else if (!strcmp(op, "greedy_round")) {                      /* [best,val,nexact] = (A,E,b,tol,it,fun,b_self,mode,screen) */
+        /* the loop body of functions/krylov_miobi.m:76-124 in one call: candidate scores + first-wins arg-min (mode 0) /
+         * arg-max (mode 1); best is the 1-based row of E (0: none).  screen = -1 reads KR_GREEDY_SCREEN. */
+        kr_matrix* M = matrix_of(prhs[0]);
+        mwSize nE = mxGetM(prhs[1]);
+        int64_t* E = to_i64(prhs[1], NULL);
+        int64_t best = -1, info[4] = {0, 0, 0, 0};
+        double val = 0.0;
+        int screen = (int)mxGetScalar(prhs[8]);
+        if (screen < 0) { const char* e = getenv("KR_GREEDY_SCREEN"); screen = (e && atoi(e) != 0) ? 1 : 0; }
+        chk(kr_greedy_round(ctx(), M, (int64_t)nE, E, mxGetScalar(prhs[2]), mxGetScalar(prhs[6]), mxGetScalar(prhs[3]),
+                            (int64_t)mxGetScalar(prhs[4]), fun_of(prhs[5]), (int)mxGetScalar(prhs[7]), screen, &best, &val,
+                            NULL, NULL, info));
+        plhs[0] = scalar((double)(best + 1));
+        if (nlhs > 1) plhs[1] = scalar(val);
+        if (nlhs > 2) plhs[2] = scalar((double)info[0]);
+        mxFree(E);
     } else if (!strcmp(op, "fun_update")) {                        /* [Xm,iter,lucky,Um] = (A,U,B,fun,tol,it,want_basis) */
         kr_matrix* M = matrix_of(prhs[0]);
         int64_t dim, it; int lucky, dense;

@@ -184,6 +184,17 @@ int main(int argc, char** argv) {
         rhs[7] = mxCreateDoubleScalar(b);
         mexFunction(3, lhs, 8, rhs);
         put(out, "edges_x_after_insert", mxGetPr(lhs[0]), nE);
+        {   /* [best,val] = kr_mex('greedy_round', h, E, b, tol, it, fun, b_self, mode, screen) on the edited matrix */
+            mxArray* gl[3] = {NULL, NULL, NULL};
+            const mxArray* gr[10];
+            double gv[3];
+            gr[0] = mxCreateString("greedy_round"); gr[1] = lh[0]; gr[2] = E; gr[3] = mxCreateDoubleScalar(b);
+            gr[4] = mxCreateDoubleScalar(tol); gr[5] = mxCreateDoubleScalar(itmax); gr[6] = mxCreateString(fun);
+            gr[7] = mxCreateDoubleScalar(b); gr[8] = mxCreateDoubleScalar(1.0); gr[9] = mxCreateDoubleScalar(0.0);
+            mexFunction(3, gl, 10, gr);
+            gv[0] = mxGetScalar(gl[0]); gv[1] = mxGetScalar(gl[1]); gv[2] = mxGetScalar(gl[2]);
+            put(out, "greedy_round_make", gv, 3);
+        }
         r3[0] = mxCreateString("matrix_free"); r3[1] = lh[0];
         mexFunction(0, lhs, 2, r3);
         mexFunction(0, lhs, 2, r3);                                  /* idempotent */

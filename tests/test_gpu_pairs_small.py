@@ -36,9 +36,11 @@ def _check(kr, O, A, E, sign, tol, it, fun="exp", every=1):
             U, B = edge_UB(n, int(E[h, 0]), int(E[h, 1]), sign)
             ox, oit, olk = O.trace_fun_update(A, U, B, tol, it, 0, fun)
             assert itv[h] == oit and bool(lucky[h]) == bool(olk), (h, itv[h], oit)
-            # relative to the value, or to the caller's stopping tolerance where the value is below it (an update of
-            # 3e-5 under tol = 1e-5 is a difference of eigenvalue sums of size 10: 1e-10 of IT is below one ulp of them)
-            assert abs(x[h] - ox) <= RTOL * max(abs(ox), tol), (h, x[h], ox)
+            # 1e-10 relative to the value, plus the rounding floor of the formula itself: Xm is a difference of two sums
+            # of ~2j terms of size f(||A||) (trace_fun_update.m:85-89), so neither the oracle nor the device can carry
+            # more than a few ulps of f(||A||) - it only shows for weak updates (here 3e-5 against sums of size 6)
+            floor = 16 * np.finfo(float).eps * tol / 1e-6 if tol > 1e-29 else 0.0
+            assert abs(x[h] - ox) <= RTOL * abs(ox) + floor, (h, x[h], ox)
     return x, itv
 
 

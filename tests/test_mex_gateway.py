@@ -119,3 +119,7 @@ def test_gateway_matches_python_binding(tmp_path):
         warnings.simplefilter("ignore")
         x2, _, _ = kr.trace_fun_update_edges(A2.tocsr(), E, 1.0, tol, 100, "exp")
     assert np.max(np.abs(out["edges_x_after_insert"] - x2) / np.abs(x2)) <= 1e-12
+    # one greedy 'make' round through the gateway (the call matlab/krylov_miobi.m makes): 1-based winner, its value, count
+    bsel, vsel = kr.select_candidate(x2, "make")
+    assert out["greedy_round_make"][0] == bsel + 1 and abs(out["greedy_round_make"][1] - vsel) <= 1e-12 * abs(vsel)
+    assert out["greedy_round_make"][2] == len(E)
