@@ -254,7 +254,7 @@ inline void ts_rightmul(kr_ctx* ctx, const PanelList& V, const PanelList& W, int
 // the reflectors read back from the strictly lower part of W.
 constexpr int HQR_MAXB = 128;        // widest block
 constexpr int HQR_THREADS = 1024;    // 32 warps, one row per warp at a time: the passes are latency-bound (a row's
-constexpr int HQR_ROWS = 128;        // reflector entry is a dependent load), so few rows per warp = 4
+constexpr int HQR_ROWS = 128;        // reflector entry is a dependent load), so few rows per warp = 4; larger n: see HqrWork::prepare
 
 struct HqrState {
     double* R;          // [bs*bs]
@@ -272,7 +272,7 @@ __device__ __forceinline__ double* hqr_at(const PanelList& W, int64_t r, int c) 
 // Factor pass k (0 <= k <= bs).  Reflector k-1 is defined by: alpha = pivot value W(k-1,k-1) (pass k-1 saved the
 // pivot row), xnorm^2 = dots[k-1], and for j >= k: d_j = dots[j] (over rows below k-1), W(k-1, j) = pivot[j].
 __global__ void __launch_bounds__(HQR_THREADS)
-hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nctas) {
+hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nctas, int rows_per_cta) {
     __shared__ double coef[HQR_MAXB];      // tau * s_j for the trailing columns of reflector k-1
     __shared__ double sdots[HQR_MAXB];
     __shared__ double wred[HQR_THREADS / 32][HQR_MAXB];
@@ -324,7 +324,7 @@ hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int n
         __syncthreads();
     }
     // rows of this CTA
-    const int64_t r0 = (int64_t)blockIdx.x * HQR_ROWS, r1 = min(n, r0 + (int64_t)HQR_ROWS);
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + (int64_t)rows_per_cta);
     const int warp = tid >> 5, lane = tid & 31;
     double acc[HQR_MAXB / 32];
 #pragma unroll
@@ -377,7 +377,7 @@ hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int n
 //   Q(k:, j) -= tau_k v_k dots[j]  (j > k);  Q(k,k) = 1 - tau_k;  Q(k+1:, k) = -tau_k v_k;  Q(0:k-1, k) = 0
 // and the pass accumulates dots'[j] = v_{k-1}' Q(k-1:, j) for j >= k for the next one.
 __global__ void __launch_bounds__(HQR_THREADS)
-hqr_formq_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nctas) {
+hqr_formq_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nctas, int rows_per_cta) {
     __shared__ double coef[HQR_MAXB];
     __shared__ double wred[HQR_THREADS / 32][HQR_MAXB];
     const int tid = threadIdx.x;
@@ -394,7 +394,7 @@ hqr_formq_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nc
     __syncthreads();
     const double tau_prev = k > 0 ? st.tau[k - 1] : 0.0;
     (void)tau_prev;
-    const int64_t r0 = (int64_t)blockIdx.x * HQR_ROWS, r1 = min(n, r0 + (int64_t)HQR_ROWS);
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + (int64_t)rows_per_cta);
     const int warp = tid >> 5, lane = tid & 31;
     double acc[HQR_MAXB / 32];
 #pragma unroll
@@ -440,10 +440,13 @@ __global__ void hqr_clear_kernel(double* p, size_t count) {
 struct HqrWork {
     DevBuf<double> buf;
     HqrState st;
-    int nctas = 0, bs = 0;
+    int nctas = 0, bs = 0, rows_per_cta = HQR_ROWS;
     void prepare(kr_ctx* ctx, int64_t n, int bs_) {
         bs = bs_;
-        nctas = (int)std::max<int64_t>(1, ceil_div(n, HQR_ROWS));
+        // every CTA of a pass first sums the previous pass' per-CTA partial dots (nctas x bs loads): keep nctas at two
+        // waves of resident CTAs instead of n / 128 (n = 200 k: 1 563 CTAs, 0.4 ms per pass, most of it that prologue)
+        rows_per_cta = (int)std::max<int64_t>(HQR_ROWS, ceil_div(ceil_div(n, (int64_t)2 * ctx->num_sms), 32) * 32);
+        nctas = (int)std::max<int64_t>(1, ceil_div(n, rows_per_cta));
         const size_t need = (size_t)bs * bs + 2 * (size_t)bs + 2 * (size_t)nctas * HQR_MAXB + 2 * HQR_MAXB;
         if (buf.count < need) buf.reset(ctx, need);
         double* d = buf.p;
@@ -462,12 +465,12 @@ inline void hqr_thin(kr_ctx* ctx, const PanelList& W, int64_t n, int bs, HqrWork
     work.prepare(ctx, n, bs);
     KR_LAUNCH(ctx, hqr_clear_kernel, 8, 256, 0, work.buf.p, work.buf.count);
     for (int k = 0; k <= bs; ++k)
-        KR_LAUNCH(ctx, hqr_factor_pass_kernel, work.nctas, HQR_THREADS, 0, W, n, bs, k, work.st, work.nctas);
+        KR_LAUNCH(ctx, hqr_factor_pass_kernel, work.nctas, HQR_THREADS, 0, W, n, bs, k, work.st, work.nctas, work.rows_per_cta);
     // dorg2r: a leading pass that only accumulates v_{bs-1}' Q(:, j) is unnecessary (no columns to the right of
     // bs-1), but the partial set read by pass bs-1 must be zero: pass k reads set (k&1)^1
     KR_LAUNCH(ctx, hqr_clear_kernel, 8, 256, 0, work.st.partial, 2 * (size_t)work.nctas * HQR_MAXB);
     for (int k = bs - 1; k >= 0; --k)
-        KR_LAUNCH(ctx, hqr_formq_pass_kernel, work.nctas, HQR_THREADS, 0, W, n, bs, k, work.st, work.nctas);
+        KR_LAUNCH(ctx, hqr_formq_pass_kernel, work.nctas, HQR_THREADS, 0, W, n, bs, k, work.st, work.nctas, work.rows_per_cta);
 }
 
 // ------------------------------------------------------------------------------------ CholQR2 + Householder signs
