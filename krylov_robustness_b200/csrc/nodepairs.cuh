@@ -184,6 +184,17 @@ node_pair_kernel(NodePairArgs a) {
     }
 }
 
+// G_0q = V_0' V_q without a pass over n: level 0 holds the unit vectors e_{node}, so G_0q(i, j) = V_q(node_i, j)
+// (5 of the 15 Grams of a 4-step screen).  grid = (dpad / 16, dpad / 16), 256 threads.
+__global__ void __launch_bounds__(256)
+node_gram0_kernel(const double* __restrict__ Vq, int64_t n, const int64_t* __restrict__ nodes, int d, int dpad,
+                  double* __restrict__ G) {
+    const int i = blockIdx.x * 16 + threadIdx.x / 16, j = blockIdx.y * 16 + threadIdx.x % 16;
+    double v = 0.0;
+    if (i < d && j < d) v = Vq[(int64_t)(j / PW) * n * PW + (nodes[i] - 1) * PW + (j % PW)];
+    G[i + (size_t)j * dpad] = v;
+}
+
 struct NodeScreenOut {
     std::vector<double> approx;
     std::vector<int> steps, status;    // status: 1 converged (approx usable), anything else -> exact path
@@ -232,9 +243,17 @@ inline NodeScreenOut node_screen_run(kr_ctx* ctx, const kr_matrix* M, const int6
     a.ci = dci.p; a.cj = dcj.p; a.np = (int)np; a.it = it; a.fun = fun;
     a.tol = tol; a.b_off = b_off; a.piv_min = 1e-3;
     a.Xstop = dX.p; a.approx = dapprox.p; a.steps = dsteps.p; a.status = dstatus.p;
+    DevBuf<int64_t> dnodes(ctx, (size_t)d);
+    dnodes.upload(nodes.data(), (size_t)d);
     auto gram = [&](int p, int q) {                               // G_pq = V_p' V_q, p <= q
         DevBuf<double>& g = G[(size_t)p * (NP_MAXL + 1) + q];
         g.reset(ctx, (size_t)dpad * dpad);
+        if (p == 0) {                                             // rows of V_q at the nodes: no contraction needed
+            KR_LAUNCH(ctx, node_gram0_kernel, dim3((unsigned)(dpad / 16), (unsigned)(dpad / 16)), 256, 0, B.V[(size_t)q]->p(), n,
+                      dnodes.p, d, dpad, g.p);
+            a.G[q] = g.p;
+            return;
+        }
         PanelList Vp, Vq;
         Vp.add(*B.V[(size_t)p]);
         Vq.add(*B.V[(size_t)q]);

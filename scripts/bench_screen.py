@@ -35,7 +35,7 @@ def main():
     out = {"candidates": int(E.shape[0]), "seconds_screened_round": dt, "edges_per_sec": E.shape[0] / dt, "info": info,
            "best_candidate": [int(x) for x in E[b]], "best_value": v, "launches": c1["launches"] - c0["launches"],
            "matvecs": c1["matvecs"] - c0["matvecs"]}
-    if os.environ.get("KR_SCREEN_EXACT"):
+    if os.environ.get("KR_SCREEN_EXACT", "0") not in ("", "0"):
         t0 = time.perf_counter()
         x, it, _ = kr.trace_fun_update_edges(M, E, 1.0 / lam, tol, 100, "exp")
         dte = time.perf_counter() - t0
