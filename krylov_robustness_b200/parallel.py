@@ -92,6 +92,67 @@ def sharded_probe_trace(local_sum_fn, k_total):
     return allreduce_sum(s) / float(k_total)
 
 
+def sharded_entries(entries_fn, omega):
+    """f(A)(i, j) for the index pairs omega (k x 2, 1-based) with the DISTINCT FIRST INDICES split across the ranks
+    (one single-vector Krylov space per distinct row, functions/function_multiple_entries.m:42,
+    86-110 - the spaces are independent, so a rank advances only its share of them).  ``entries_fn(omega_part) ->
+    (values, iter)`` is the per-rank evaluator (functions.function_multiple_entries on the device).  Returns the full
+    value vector in the order of omega on every rank and the largest step count (one all-gather of the disjoint
+    values + one all-reduce of an int)."""
+    rank, world = _world()
+    omega = np.atleast_2d(np.asarray(omega)).astype(np.int64)
+    k = omega.shape[0]
+    first = omega[:, 0]
+    uniq, inv = np.unique(first, return_inverse=True)          # the split must be the same on every rank
+    lo, hi = shard_bounds(uniq.size)
+    mine = np.nonzero((inv >= lo) & (inv < hi))[0]
+    if mine.size:
+        vals, it = entries_fn(omega[mine])
+        vals, it = np.asarray(vals, dtype=np.float64), int(it)
+    else:
+        vals, it = np.zeros(0), 0
+    if world == 1:
+        return vals, it
+    # disjoint contributions: scatter into a zero vector and sum (every pair is owned by exactly one rank)
+    full = torch.zeros(k, dtype=torch.float64, device=_device())
+    if mine.size:
+        full[torch.from_numpy(mine).to(full.device)] = torch.from_numpy(vals).to(full.device)
+    dist.all_reduce(full, op=dist.ReduceOp.SUM)
+    itmax = torch.tensor([it], dtype=torch.int64, device=_device())
+    dist.all_reduce(itmax, op=dist.ReduceOp.MAX)
+    return full.cpu().numpy(), int(itmax.item())
+
+
+def sharded_expmv(expmv_fn, b):
+    """e^{tA} b with the COLUMNS of b (n x q) split across the ranks.  The Taylor recurrences
+    of the columns are independent once the degree m and the scaling s are fixed, but the early-termination test of
+    functions/expmv.m:83 uses matrix inf-norms over ALL columns - so the per-rank evaluator must run with
+    ``full_term=True`` (every rank then computes exactly the terms a single-GPU full_term run computes for its
+    columns; SURVEY.md 8e names this option) and must be given the degree table M of the FULL block (select_taylor_degree
+    looks at size(b, 2), functions/select_taylor_degree.m:44).  ``expmv_fn(b_part) -> f_part``.  Returns the full n x q
+    result on every rank (one all-gather)."""
+    rank, world = _world()
+    b = np.asarray(b, dtype=np.float64)
+    if b.ndim == 1:
+        b = b[:, None]
+    n, q = b.shape
+    lo, hi = shard_bounds(q)
+    fpart = np.asarray(expmv_fn(b[:, lo:hi]), dtype=np.float64).reshape(n, hi - lo) if hi > lo else np.zeros((n, 0))
+    if world == 1:
+        return fpart
+    cap = -(-q // world)
+    buf = torch.zeros((cap, n), dtype=torch.float64, device=_device())
+    if hi > lo:
+        buf[:hi - lo] = torch.from_numpy(np.ascontiguousarray(fpart.T)).to(buf.device)
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    cols = []
+    for r in range(world):
+        l, h = shard_bounds(q, r, world)
+        cols.append(out[r][:h - l].cpu().numpy().T)
+    return np.concatenate(cols, axis=1)
+
+
 def bind_to_gpu_numa_node(device_index):
     """Pin this process (CPU affinity, hence first-touch page placement of everything allocated afterwards,
     pinned staging buffers included) to the NUMA node the GPU hangs off.  On a two-socket host a rank whose

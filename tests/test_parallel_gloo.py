@@ -50,7 +50,14 @@ def _worker(rank, world, port, q):
     As = A / 8.0
     tr = P.sharded_probe_trace(lambda lo, hi: O.slq_trace(As, Z[:, lo:hi], 12, "exp")[1].sum(), 7)
     lo, hi = P.shard_bounds(11)
-    q.put((rank, vals.tolist(), best, bestval, tr, (lo, hi)))
+    # C2 sharding: distinct first indices of omega split across the ranks (pairs repeat first indices on purpose)
+    Om = np.array([[5, 9], [17, 3], [5, 40], [201, 7], [17, 17], [88, 2], [201, 5]], dtype=np.int64)
+    ent, ent_it = P.sharded_entries(lambda om: O.function_multiple_entries(As, om, "exp", 1e-12, 60), Om)
+    # C4 sharding: right-hand-side columns split, full_term evaluators, degree table of the FULL block
+    Bm = np.random.default_rng(5).standard_normal((n, 5))
+    Mtab = O.select_taylor_degree(As, Bm)[0]
+    fexp = P.sharded_expmv(lambda bp: O.expmv(1.0, As, bp, Mtab, "double", True, False, True)[0], Bm)
+    q.put((rank, vals.tolist(), best, bestval, tr, (lo, hi), ent.tolist(), ent_it, fexp.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -81,10 +88,17 @@ def test_two_rank_sharding_matches_serial(graphs):
     Z = np.sign(np.random.default_rng(3).standard_normal((n, 7)))
     tr_serial = O.slq_trace(A / 8.0, Z, 12, "exp")[0]
     assert res[0][5] == (0, 6) and res[1][5] == (6, 11)
-    for rank, vals, best, bestval, tr, _ in res:
+    Om = np.array([[5, 9], [17, 3], [5, 40], [201, 7], [17, 17], [88, 2], [201, 5]], dtype=np.int64)
+    ent_serial, it_serial = O.function_multiple_entries(A / 8.0, Om, "exp", 1e-12, 60)
+    Bm = np.random.default_rng(5).standard_normal((n, 5))
+    Mtab = O.select_taylor_degree(A / 8.0, Bm)[0]
+    f_serial = O.expmv(1.0, A / 8.0, Bm, Mtab, "double", True, False, True)[0]
+    for rank, vals, best, bestval, tr, _, ent, ent_it, fexp in res:
         assert vals == serial                       # identical full vector on every rank
         assert best == int(np.argmin(serial)) and bestval == min(serial)
         assert abs(tr - tr_serial) <= 1e-12 * abs(tr_serial)
+        assert np.array_equal(np.array(ent), ent_serial) and ent_it == it_serial      # spaces are independent
+        assert np.array_equal(np.array(fexp), f_serial)                               # columns are independent (full_term)
 
 
 def test_shard_bounds_cover_everything():
