@@ -32,7 +32,11 @@ constexpr int NP_THREADS = 64;
 constexpr int NP_MAXNN = 2 * NP_MAXL;  // largest pair problem
 
 struct NodePairArgs {
-    const double* G[(NP_MAXL + 1) * (NP_MAXL + 1)];   // G[a*(NP_MAXL+1)+b], a <= b: V_a' V_b (dpad x dpad column-major)
+    // G[a*(NP_MAXL+1)+b] = V_a' V_b, column-major with leading dimension dpad.  Full mode: a <= b only, all dpad columns
+    // (the transposed block serves a > b).  Restricted mode (jcol0 >= 0): every ordered (a, b), columns jcol0 .. dpad
+    // only - the second end points of a rank's candidate shard are few, the first ones are not.
+    const double* G[(NP_MAXL + 1) * (NP_MAXL + 1)];
+    int jcol0;
     const double* Hc;                                 // ArnoldiBatch::Hc: [node][step][0..it1]
     int it1, dpad, L;                                 // L = shared steps available (levels 0..L)
     const int* ci;                                    // [np] node column of end point i
@@ -65,7 +69,8 @@ node_pair_kernel(NodePairArgs a) {
     const int L1 = a.L + 1, W = NP_MAXL + 1;
     for (int e = tid; e < L1 * L1; e += NP_THREADS) {
         const int p = e / L1, q = e % L1;
-        S[p * W + q] = p <= q ? a.G[p * W + q][ni + (size_t)nj * a.dpad] : a.G[q * W + p][nj + (size_t)ni * a.dpad];
+        if (a.jcol0 >= 0) S[p * W + q] = a.G[p * W + q][ni + (size_t)(nj - a.jcol0) * a.dpad];
+        else S[p * W + q] = p <= q ? a.G[p * W + q][ni + (size_t)nj * a.dpad] : a.G[q * W + p][nj + (size_t)ni * a.dpad];
     }
     for (int e = tid; e < L1 * a.L; e += NP_THREADS) {
         const int r = e / a.L, col = e % a.L;                    // Hbar(r, col), nonzero for r <= col + 1
@@ -184,21 +189,26 @@ node_pair_kernel(NodePairArgs a) {
     }
 }
 
-// G_0q = V_0' V_q without a pass over n: level 0 holds the unit vectors e_{node}, so G_0q(i, j) = V_q(node_i, j)
-// (5 of the 15 Grams of a 4-step screen).  grid = (dpad / 16, dpad / 16), 256 threads.
+// Grams against level 0 without a pass over n: level 0 holds the unit vectors e_{node}, so
+//   G_0q(i, j) = V_q(node_i, j)   (transposed == 0)        G_p0(i, j) = V_p(node_j, i)   (transposed != 0)
+// for the columns j = jcol0 .. dpad (5 of the 15 Grams of a 4-step screen).  grid = (dpad / 16, cols / 16), 256 threads.
 __global__ void __launch_bounds__(256)
-node_gram0_kernel(const double* __restrict__ Vq, int64_t n, const int64_t* __restrict__ nodes, int d, int dpad,
-                  double* __restrict__ G) {
-    const int i = blockIdx.x * 16 + threadIdx.x / 16, j = blockIdx.y * 16 + threadIdx.x % 16;
+node_gram0_kernel(const double* __restrict__ Vx, int64_t n, const int64_t* __restrict__ nodes, int d, int dpad, int jcol0,
+                  int transposed, double* __restrict__ G) {
+    const int i = blockIdx.x * 16 + threadIdx.x / 16, jj = blockIdx.y * 16 + threadIdx.x % 16, j = jcol0 + jj;
     double v = 0.0;
-    if (i < d && j < d) v = Vq[(int64_t)(j / PW) * n * PW + (nodes[i] - 1) * PW + (j % PW)];
-    G[i + (size_t)j * dpad] = v;
+    if (i < d && j < d) {
+        const int row = transposed ? j : i, col = transposed ? i : j;
+        v = Vx[(int64_t)(col / PW) * n * PW + (nodes[row] - 1) * PW + (col % PW)];
+    }
+    G[i + (size_t)jj * dpad] = v;
 }
 
 struct NodeScreenOut {
     std::vector<double> approx;
     std::vector<int> steps, status;    // status: 1 converged (approx usable), anything else -> exact path
     int distinct_nodes = 0, levels = 0;
+    bool restricted = false;           // Grams restricted to the column window of the "j" end points
 };
 
 // can the screen be used at all for this candidate list?
@@ -216,17 +226,31 @@ inline NodeScreenOut node_screen_run(kr_ctx* ctx, const kr_matrix* M, const int6
     NodeScreenOut out;
     const CsrDev& A = M->dev;
     const int64_t n = A.n;
-    std::vector<int64_t> nodes;
-    nodes.reserve((size_t)2 * np);
-    for (int64_t q = 0; q < np; ++q) { nodes.push_back(Ei[q]); nodes.push_back(Ej[q]); }
-    std::sort(nodes.begin(), nodes.end());
-    nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+    // Orientation: the side with fewer distinct end points becomes "j" (the score is symmetric in the end points);
+    // node columns: nodes that only occur as "i" first, the "j" nodes last, so that the j side is a column window.
+    std::vector<int64_t> si(Ei, Ei + np), sj(Ej, Ej + np);
+    std::sort(si.begin(), si.end());
+    si.erase(std::unique(si.begin(), si.end()), si.end());
+    std::sort(sj.begin(), sj.end());
+    sj.erase(std::unique(sj.begin(), sj.end()), sj.end());
+    const bool swap_sides = si.size() < sj.size();
+    if (swap_sides) std::swap(si, sj);
+    std::vector<int64_t> nodes;                        // column order
+    for (int64_t v : si)
+        if (!std::binary_search(sj.begin(), sj.end(), v)) nodes.push_back(v);
+    const int jstart = (int)nodes.size();
+    nodes.insert(nodes.end(), sj.begin(), sj.end());
     const int d = (int)nodes.size();
     out.distinct_nodes = d;
+    auto col_of = [&](int64_t v) -> int {
+        auto jt = std::lower_bound(sj.begin(), sj.end(), v);
+        if (jt != sj.end() && *jt == v) return jstart + (int)(jt - sj.begin());
+        return (int)(std::lower_bound(nodes.begin(), nodes.begin() + jstart, v) - nodes.begin());
+    };
     std::vector<int> ci((size_t)np), cj((size_t)np);
     for (int64_t q = 0; q < np; ++q) {
-        ci[(size_t)q] = (int)(std::lower_bound(nodes.begin(), nodes.end(), Ei[q]) - nodes.begin());
-        cj[(size_t)q] = (int)(std::lower_bound(nodes.begin(), nodes.end(), Ej[q]) - nodes.begin());
+        ci[(size_t)q] = col_of(swap_sides ? Ej[q] : Ei[q]);
+        cj[(size_t)q] = col_of(swap_sides ? Ei[q] : Ej[q]);
     }
     const int Lmax = std::min(it, NP_MAXL);
     ArnoldiBatch B(ctx, A, nodes, Lmax);
@@ -245,20 +269,27 @@ inline NodeScreenOut node_screen_run(kr_ctx* ctx, const kr_matrix* M, const int6
     a.Xstop = dX.p; a.approx = dapprox.p; a.steps = dsteps.p; a.status = dstatus.p;
     DevBuf<int64_t> dnodes(ctx, (size_t)d);
     dnodes.upload(nodes.data(), (size_t)d);
-    auto gram = [&](int p, int q) {                               // G_pq = V_p' V_q, p <= q
+    // restricted mode pays (L+1)^2 Grams of dpad x jcols instead of (L+1)(L+2)/2 of dpad x dpad
+    const int jpanel0 = jstart / PW, jcols = dpad - jpanel0 * PW;
+    bool restricted = jcols * 20 <= dpad * 11;
+    if (const char* e = getenv("KR_SCREEN_RESTRICT")) restricted = atoi(e) != 0;
+    a.jcol0 = restricted ? jpanel0 * PW : -1;
+    out.restricted = restricted;
+    const int gcol0 = restricted ? jpanel0 * PW : 0, gcols = restricted ? jcols : dpad;
+    auto gram = [&](int p, int q) {                               // G_pq = V_p' V_q(:, gcol0 ..)
         DevBuf<double>& g = G[(size_t)p * (NP_MAXL + 1) + q];
-        g.reset(ctx, (size_t)dpad * dpad);
-        if (p == 0) {                                             // rows of V_q at the nodes: no contraction needed
-            KR_LAUNCH(ctx, node_gram0_kernel, dim3((unsigned)(dpad / 16), (unsigned)(dpad / 16)), 256, 0, B.V[(size_t)q]->p(), n,
-                      dnodes.p, d, dpad, g.p);
-            a.G[q] = g.p;
+        g.reset(ctx, (size_t)dpad * gcols);
+        a.G[p * (NP_MAXL + 1) + q] = g.p;
+        if (p == 0 || q == 0) {                                   // rows of a level at the nodes: no contraction needed
+            KR_LAUNCH(ctx, node_gram0_kernel, dim3((unsigned)(dpad / 16), (unsigned)(gcols / 16)), 256, 0,
+                      B.V[(size_t)(p == 0 ? q : p)]->p(), n, dnodes.p, d, dpad, gcol0, p == 0 ? 0 : 1, g.p);
             return;
         }
         PanelList Vp, Vq;
         Vp.add(*B.V[(size_t)p]);
-        Vq.add(*B.V[(size_t)q]);
+        const PanelBuf& bq = *B.V[(size_t)q];
+        for (int pq = gcol0 / PW; pq < bq.panels; ++pq) Vq.p[Vq.count++] = bq.p() + (int64_t)pq * n * PW;
         ts_gram(ctx, Vp, Vq, n, g.p, gscratch);
-        a.G[p * (NP_MAXL + 1) + q] = g.p;
     };
     gram(0, 0);
     int L = 0, evaluated = 0;
@@ -269,6 +300,8 @@ inline NodeScreenOut node_screen_run(kr_ctx* ctx, const kr_matrix* M, const int6
         for (; L < target; ++L) {
             B.step(L);
             for (int p = 0; p <= L + 1; ++p) gram(p, L + 1);
+            if (restricted)
+                for (int q = 0; q <= L; ++q) gram(L + 1, q);
         }
         a.L = L;
         a.s0 = evaluated + 1;

@@ -35,7 +35,7 @@ def _omega(A, k, seed, min_degree=3):
 
 # ------------------------------------------------------------------ L1
 @pytest.mark.parametrize("arnoldi", [False, True])
-@pytest.mark.parametrize("bs", [1, 2, 5])
+@pytest.mark.parametrize("bs", [1, 2, 5, 24])
 def test_krylov_basis_invariants(kr, O, graphs, arnoldi, bs):
     A = graphs("oregon_A1")
     n = A.shape[0]
@@ -68,6 +68,11 @@ def test_krylov_basis_invariants(kr, O, graphs, arnoldi, bs):
     assert np.max(np.abs(ev - oev)) <= RTOL * np.max(np.abs(oev))
     # Householder conventions match LAPACK's, so even the block entries agree up to rounding
     assert np.allclose(np.abs(H), np.abs(oH), rtol=1e-8, atol=1e-10 * np.abs(oH).max())
+    # ... SIGNS included: the thin QR is two rounds of Cholesky QR on the tensor cores whose column signs are
+    # reconstructed to be those of dgeqr2 / dorg2r (tsdense.cuh::thin_qr), so V and H are the reference's, not just
+    # a sign-flipped equivalent
+    assert np.allclose(H, oH, rtol=1e-8, atol=1e-10 * np.abs(oH).max())
+    assert np.allclose(V, oV, rtol=0, atol=1e-9)
 
 
 def test_krylov_errors(kr, graphs):

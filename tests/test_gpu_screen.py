@@ -89,3 +89,20 @@ def test_sparse_candidate_lists_bypass_the_screen(kr, graphs):
     assert mask.all() and info["screened"] == 0
     x, _, _ = kr.trace_fun_update_edges(A, E, -1.0, 1e-6 * float(np.exp(nrm)), 100, "exp")
     assert (b, v) == kr.select_candidate(x, "break")
+
+
+@pytest.mark.parametrize("restrict", ["0", "1"])
+def test_screen_gram_modes_agree(kr, setup, monkeypatch, restrict):
+    """The cross Grams are computed either for all node pairs (full mode) or only for the column window of the shard's
+    second end points (restricted mode, what a rank of a multi-GPU round runs): same winner, same value, screen scores
+    equal to the screen's own accuracy."""
+    A, M, lam, E, O = setup
+    tol = 1e-6 * float(np.e)
+    monkeypatch.setenv("KR_SCREEN_RESTRICT", restrict)
+    shard = E[2000:3000]                            # a late shard: few second end points, many first ones
+    b, v, scores, mask, info = kr.greedy_round(M, shard, 1.0 / lam, tol, 100, "exp", "make", screen=True)
+    monkeypatch.delenv("KR_SCREEN_RESTRICT")
+    x, _, _ = kr.trace_fun_update_edges(M, shard, 1.0 / lam, tol, 100, "exp")
+    assert (b, v) == kr.select_candidate(x, "make")
+    assert info["screened"] > 0.9 * len(shard)
+    assert np.max(np.abs(scores - x) / np.abs(x)) <= 1e-6
