@@ -209,7 +209,12 @@ def test_trace_fun_update_edge_set(kr, O, graphs):
     ox, oit, _ = O.trace_fun_update(A, U.toarray(), B, tol)
     x, it, _ = kr.trace_fun_update(A, U.toarray(), B, tol)
     assert it == oit
-    assert abs(x - ox) <= 1e-8 * abs(ox)      # wide-block Lanczos drifts (see oracle tests); same drift, looser bar
+    # 7e-14 measured (scripts/diag_edge_set_tol.py): with the hand-written wide-block step the device follows the
+    # reference's arithmetic closely enough for the contract's 1e-10 here (round 1: 1e-8 with cuBLAS/cuSOLVER orderings).
+    # Blocks that turn numerically rank deficient (Oregon A0 with this selection: step 3) are the documented exception -
+    # LAPACK normalises rounding noise there and the reference's own value is only defined to ~1e-2
+    # (scripts/diag_edge_set_steps.py).
+    assert abs(x - ox) <= RTOL * abs(ox)
 
 
 # ------------------------------------------------------------------ fun_update / entries / gradients
