@@ -651,15 +651,9 @@ normest_small_kernel(CsrDevView A, CsrDevView At, double tol, double* __restrict
         __syncthreads();
         return s_val;
     };
+    const int splitA = cta_spmv_split(A), splitT = cta_spmv_split(At);
     auto spmv_cta = [&](const CsrDevView& S, const double* in, double* o) {
-        for (int g = warp; g < n; g += 32) {                    // one warp per stored row
-            const int p0 = S.row_ptr[g], p1 = S.row_ptr[g + 1];
-            double s = 0.0;
-            for (int p = p0 + lane; p < p1; p += 32) s += (S.val ? S.val[p] : S.uval) * in[S.col[p]];
-            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) o[S.row_order[g]] = s;
-        }
-        __syncthreads();
+        cta_spmv<1024>(S, in, o, nullptr, &S == &A ? splitA : splitT);
     };
     // x = sum(abs(S), 1)' = abs-sums of the columns of S = row abs-sums of S'
     for (int g = warp; g < n; g += 32) {
@@ -742,19 +736,8 @@ power_iteration_small_kernel(CsrDevView A, int mode, double tol, int maxit, doub
         __syncthreads();
         return s_val;
     };
-    auto spmv_cta = [&](const double* in, double* o, const double* scale) {
-        for (int g = warp; g < n; g += 32) {
-            const int p0 = A.row_ptr[g], p1 = A.row_ptr[g + 1];
-            double s = 0.0;
-            for (int p = p0 + lane; p < p1; p += 32) {
-                const int c = A.col[p];
-                s += (A.val ? A.val[p] : A.uval) * (scale ? in[c] * scale[c] : in[c]);
-            }
-            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) o[A.row_order[g]] = s;
-        }
-        __syncthreads();
-    };
+    const int split = cta_spmv_split(A);
+    auto spmv_cta = [&](const double* in, double* o, const double* scale) { cta_spmv<1024>(A, in, o, scale, split); };
     if (mode == 1) {        // dinv = 1 ./ sum(A) (column sums = row sums of the symmetric A)
         for (int g = warp; g < n; g += 32) {
             double s = 0.0;

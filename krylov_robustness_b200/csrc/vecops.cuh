@@ -27,6 +27,70 @@ spmv_kernel(CsrDevView A, const double* __restrict__ x, double* __restrict__ y, 
     }
 }
 
+// ---- one-CTA products for the whole-loop kernels of small graphs (normest, power iteration): latency-bound, so the
+// rows a lane group has in flight matter more than anything else.  Rows are stored by decreasing length:
+// cta_spmv_split finds the first stored row with at most 32 nonzeros (every thread runs the same binary search),
+// rows before it get a warp each, the rest four lanes each with four rows of a lane group in flight.
+__device__ __forceinline__ int cta_spmv_split(const CsrDevView& S) {
+    int lo = 0, hi = S.n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (S.row_ptr[mid + 1] - S.row_ptr[mid] > 32) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// out[row] = sum_p val[p] * in[col[p]] * (scale ? scale[col[p]] : 1); all NT threads call; ends with a CTA barrier
+template <int NT>
+__device__ __forceinline__ void cta_spmv(const CsrDevView& S, const double* in, double* out, const double* scale, int split) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool hv = S.val != nullptr;
+    for (int g = warp; g < split; g += NT / 32) {
+        const int p0 = S.row_ptr[g], p1 = S.row_ptr[g + 1];
+        double s = 0.0;
+#pragma unroll 4
+        for (int p = p0 + lane; p < p1; p += 32) {
+            const int c = S.col[p];
+            s += (hv ? S.val[p] : 1.0) * (scale ? in[c] * scale[c] : in[c]);
+        }
+        for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) out[S.row_order[g]] = hv ? s : s * S.uval;
+    }
+    constexpr int G = NT / 4, ILP = 4;
+    const int sub = lane & 3;
+    for (int base = split + warp * 8; base < S.n; base += G * ILP) {
+        int q0[ILP], q1[ILP];
+        double acc[ILP];
+        int maxlen = 0;
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const int r = base + u * G + (lane >> 2);
+            q0[u] = q1[u] = 0;
+            acc[u] = 0.0;
+            if (r < S.n) { q0[u] = S.row_ptr[r]; q1[u] = S.row_ptr[r + 1]; }
+            maxlen = max(maxlen, q1[u] - q0[u]);
+        }
+        for (int off = sub; off < maxlen; off += 4) {
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                const int p = q0[u] + off;
+                if (p < q1[u]) {
+                    const int c = S.col[p];
+                    acc[u] += (hv ? S.val[p] : 1.0) * (scale ? in[c] * scale[c] : in[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const int r = base + u * G + (lane >> 2);
+            double v = acc[u];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (sub == 0 && r < S.n) out[S.row_order[r]] = hv ? v : v * S.uval;
+        }
+    }
+    __syncthreads();
+}
+
 inline void spmv(kr_ctx* ctx, const CsrDev& A, const double* x, double* y, double alpha = 1.0, double mu = 0.0) {
     if (A.n == 0) return;
     KR_LAUNCH(ctx, spmv_kernel, (int)ceil_div(A.n * 8, 256), 256, 0, A.view(), x, y, alpha, mu);
