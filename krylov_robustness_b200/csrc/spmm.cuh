@@ -499,7 +499,7 @@ __device__ __forceinline__ Vec<CPL> gather_accumulate(int p_first, int p_end, in
 }
 
 // Multi-row tile: indices are already staged in shared memory; every row gets L lanes.
-template <int L, bool HAS_VAL, int U, class Epi>
+template <int L, bool HAS_VAL, int U, bool DELTA, class Epi>
 __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict__ srp, const int* __restrict__ srid,
                                           const int* __restrict__ scol, const double* __restrict__ sval,
                                           const double* __restrict__ Xp, double uval, Epi& epi, const CsrDevView& A,
@@ -547,7 +547,7 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict
 #pragma unroll
             for (int i = 0; i < CPL; ++i) acc.v[i] *= uval;
         }
-        if (e1 > e0 && emit) {            // pending edge edits of this tile (kr_matrix_set_edges): y_row += delta * x_col
+        if (DELTA && e1 > e0 && emit) {   // pending edge edits of this tile (kr_matrix_set_edges): y_row += delta * x_col
             for (int e = e0; e < e1; ++e)
                 if (A.dl_rowlocal[e] == rr) {
                     const Vec<CPL> x = ld_x<CPL>(xs + (int64_t)A.dl_col[e] * PW);
@@ -561,29 +561,26 @@ __device__ __forceinline__ void spmm_tile(const RowTile t, const int* __restrict
     }
 }
 
-// grid = (ntiles, panels); X panel q at X + q*n*PW.  `done` (may be null): skip everything if set.
-template <class Epi, bool HAS_VAL, int U>
-__global__ void __launch_bounds__(SPMM_THREADS, SPMM_MIN_CTAS)
-spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t panel_stride,
-            const int* __restrict__ done, const int* __restrict__ panel_active) {
+// One work item = (tile, panel): the CTA stages the tile's indices, serves its rows for this panel and writes the
+// epilogue's per-CTA partials.
+template <class Epi, bool HAS_VAL, int U, bool DELTA>
+__device__ __forceinline__ void spmm_item(const CsrDevView& A, const double* __restrict__ X, const Epi& epi_proto,
+                                          int64_t panel_stride, int tile, int panel, double* red, unsigned char* dyn_smem) {
     constexpr int CPL = Epi::CPL;
     constexpr int LP = PW / CPL;
-    if (done && *done) return;
-    const int panel = blockIdx.y;
-    if (panel_active && !panel_active[panel]) return;   // every column of this panel has converged
-    __shared__ double red[SPMM_WARPS * LPT * 8];
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
     int* scol = reinterpret_cast<int*>(dyn_smem);
     int* srp = scol + SPMM_CAP;
     int* srid = srp + SPMM_MAX_ROWS + 1;
     double* sval = reinterpret_cast<double*>(dyn_smem + SPMM_SMEM_PATTERN);
-    const int tile = blockIdx.x;
     const RowTile t = A.tiles[tile];
     const int pb = __ldg(A.row_ptr + t.start);
     const int nz = __ldg(A.row_ptr + t.start + t.count) - pb;
     const bool long_row = t.lanes_log2 == 6;   // class 6: one row, whole CTA
-    const int e0 = A.dl_tile_begin ? A.dl_tile_begin[tile] : 0;
-    const int e1 = A.dl_tile_begin ? A.dl_tile_begin[tile + 1] : 0;
+    // pending edge edits (kr_matrix_set_edges) are a template flavour of their own: carrying the (empty) range through
+    // the row loop costs the Lanczos flavour 0.7 ms per k = 512 launch (7.86 -> 7.17 ms, profiles/r02ah_*) - the
+    // kernel sits at the 64-register cap and the two live values displace gathers in flight
+    const int e0 = DELTA && A.dl_tile_begin ? A.dl_tile_begin[tile] : 0;
+    const int e1 = DELTA && A.dl_tile_begin ? A.dl_tile_begin[tile + 1] : 0;
     Epi epi = epi_proto;
     epi.init(panel, panel_stride);
     const double* Xp = X + (int64_t)panel * panel_stride;
@@ -596,10 +593,10 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
             for (int p = threadIdx.x; p < nz; p += SPMM_THREADS) sval[p] = ld_stream(A.val + pb + p);
         __syncthreads();
         switch (t.lanes_log2) {          // slots per row = 1 << lanes_log2, lanes per row = LP << lanes_log2 (<= 32)
-            case 0: spmm_tile<LP, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
-            case 1: spmm_tile<2 * LP, HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
-            case 2: spmm_tile<(4 * LP > 32 ? 32 : 4 * LP), HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
-            default: spmm_tile<(8 * LP > 32 ? 32 : 8 * LP), HAS_VAL, U>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
+            case 0: spmm_tile<LP, HAS_VAL, U, DELTA>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
+            case 1: spmm_tile<2 * LP, HAS_VAL, U, DELTA>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
+            case 2: spmm_tile<(4 * LP > 32 ? 32 : 4 * LP), HAS_VAL, U, DELTA>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
+            default: spmm_tile<(8 * LP > 32 ? 32 : 8 * LP), HAS_VAL, U, DELTA>(t, srp, srid, scol, sval, Xp, A.uval, epi, A, e0, e1); break;
         }
     } else {
         // one long row, whole CTA: stage the indices chunk by chunk, SPMM_THREADS / LP nonzero slots
@@ -625,7 +622,7 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
         Vec<CPL> acc;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) acc.v[i] = HAS_VAL ? v[i] : v[i] * A.uval;
-        if (e1 > e0 && emit) {
+        if (DELTA && e1 > e0 && emit) {
             for (int e = e0; e < e1; ++e) {      // a long-row tile holds one row: every entry is its
                 const Vec<CPL> x = ld_x<CPL>(Xp + sub * CPL + (int64_t)A.dl_col[e] * PW);
                 const double d = A.dl_val[e];
@@ -640,6 +637,24 @@ spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t p
     epi.finish(tile, panel, red);
 }
 
+// grid = (ntiles, panels); X panel q at X + q*n*PW.  `done` (may be null): skip everything if set.
+template <class Epi, bool HAS_VAL, int U, bool DELTA>
+__global__ void __launch_bounds__(SPMM_THREADS, SPMM_MIN_CTAS)
+spmm_kernel(CsrDevView A, const double* __restrict__ X, Epi epi_proto, int64_t panel_stride,
+            const int* __restrict__ done, const int* __restrict__ panel_active) {
+    if (done && *done) return;
+    const int panel = blockIdx.y;
+    if (panel_active && !panel_active[panel]) return;   // every column of this panel has converged
+    __shared__ double red[SPMM_WARPS * LPT * 8];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    spmm_item<Epi, HAS_VAL, U, DELTA>(A, X, epi_proto, panel_stride, (int)blockIdx.x, panel, red, dyn_smem);
+}
+
+// A persistent flavour (SMs x 4 CTAs walking the (panel, tile) items in order, no CTA launch / drain per item) was
+// measured and removed: 9.35 ms against 6.40 ms per k = 512 launch (profiles/r02ag_spmm_variants.jsonl) - the
+// hardware's dynamic CTA scheduler balances the very unequal tiles (a hub row against 1 024 short rows), a static
+// round-robin does not, and the per-item CTA barrier stalls the warps that finish early.
+
 // per-device one-time setup flag (cudaFuncSetAttribute applies to the current device's context)
 inline bool first_use_on_device(bool (&flags)[64], int device) {
     if (device < 0 || device >= 64 || flags[device]) return false;
@@ -652,13 +667,20 @@ inline void launch_spmm_impl(kr_ctx* ctx, const CsrDev& A, const double* X, int 
                              const int* done, const int* panel_active) {
     static bool attr_set[64] = {};              // one table per Epi instantiation
     if (first_use_on_device(attr_set, ctx->device)) {
-        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, false, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_PATTERN));
-        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, true, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_VALUED));
+        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, false, U, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_PATTERN));
+        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, true, U, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_VALUED));
+        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, false, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_PATTERN));
+        KR_CUDA(cudaFuncSetAttribute(spmm_kernel<Epi, true, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMM_SMEM_VALUED));
     }
     const int64_t ps = (int64_t)A.n * PW;
     const dim3 grid((unsigned)A.ntiles, (unsigned)panels);
-    if (A.pattern_only) spmm_kernel<Epi, false, U><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, panel_active);
-    else spmm_kernel<Epi, true, U><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, panel_active);
+    if (A.dl_count > 0) {
+        if (A.pattern_only) spmm_kernel<Epi, false, U, true><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, panel_active);
+        else spmm_kernel<Epi, true, U, true><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, panel_active);
+    } else {
+        if (A.pattern_only) spmm_kernel<Epi, false, U, false><<<grid, SPMM_THREADS, SPMM_SMEM_PATTERN, ctx->stream>>>(A.view(), X, epi, ps, done, panel_active);
+        else spmm_kernel<Epi, true, U, false><<<grid, SPMM_THREADS, SPMM_SMEM_VALUED, ctx->stream>>>(A.view(), X, epi, ps, done, panel_active);
+    }
 }
 
 #ifndef KR_SPMM_U2
