@@ -213,7 +213,7 @@ struct EpiDotT {
         else if (sub == 0) prefetch_l1(X + (int64_t)r * PW);
     }
     __device__ __forceinline__ void row(int r, int sub, Vec<CPL> y, unsigned) {
-        if (CPL != 2) xr = ld_row<CPL>(X + (int64_t)r * PW + sub * CPL);
+        if (CPL != 2) xr = ld_row<CPL>(X + (int64_t)r * PW + sub * CPL);      // (a non-volatile load here: no gain, profiles/r02aj_*)
 #pragma unroll
         for (int i = 0; i < CPL; ++i) acc[i] += xr.v[i] * y.v[i];
         st_stream(Y + (int64_t)r * PW + sub * CPL, y);
