@@ -437,7 +437,7 @@ def run_ours(args):
                     if r[0] >= 0 and r[1] > best_v:
                         best_i, best_v = int(r[0]), float(r[1])
                 return best_i, best_v, rows, sc, mask
-            screened_round(E[:4000 * world])
+            screened_round(E)                        # warm-up at full size (pool blocks of the round's own shapes)
             ms_scr, (bi, bv, rows, sc, mask) = timed(lambda: screened_round(E), 1)
             ex_best = int(np.argmax(vals))
             lo, hi = P.shard_bounds(E.shape[0])
