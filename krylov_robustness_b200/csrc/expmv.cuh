@@ -198,19 +198,34 @@ inline OneNormEst onenormest_power(kr_ctx* ctx, const kr_matrix* M, double scale
             if (b == fin) b = &t;
         }
     };
+    // Higham & Tisseur (2000), Algorithm 2.4 in the order of MathWorks' normest1.m for t = 1: estimate, test on the
+    // estimate, the PARALLEL-SIGN test (before the transposed product, which it saves), the test of max|z| against the
+    // entry of the unit vector in use, ties of max|z| to the LAST index (normest1 reverses an ascending sort).
+    // Pinned against the reference's own normAm.m run on a matrix with a negative diagonal
+    // (tests/golden/reference_golden.json: A0_loops_expmv_info, A0_loops_normAm5).
     int nprod = 0;
     double est_old = 0.0;
-    std::vector<int> hist;
-    std::vector<double> hy((size_t)n * PW), hz((size_t)n * PW);
-    for (int itn = 1; itn <= 5; ++itn) {
+    std::vector<int64_t> hist;
+    std::vector<double> hy((size_t)n * PW), hz((size_t)n * PW), hs_old((size_t)n, 0.0);
+    int64_t est_j = -1, cur = -1;
+    for (int itn = 1;; ++itn) {
         power(M->dev, x, y);
         nprod += 1;
         y.buf.download(hy.data(), hy.size());
         double est = 0.0;
         for (int64_t i = 0; i < n; ++i) est += std::abs(hy[i * PW]);
-        if (itn > 1 && est <= est_old) break;
+        if (est > est_old || itn == 2) est_j = cur;
+        if (itn >= 2 && est <= est_old) break;
         est_old = est;
-        for (int64_t i = 0; i < n; ++i) hy[i * PW] = hy[i * PW] < 0 ? -1.0 : 1.0;
+        if (itn > 5) break;
+        double ss = 0.0;
+        for (int64_t i = 0; i < n; ++i) {
+            const double sg = hy[i * PW] < 0 ? -1.0 : 1.0;
+            ss += sg * hs_old[i];
+            hs_old[i] = sg;
+            hy[i * PW] = sg;
+        }
+        if (std::abs(ss) == (double)n) break;
         y.buf.upload(hy.data(), hy.size());
         PanelBuf s2(ctx, n, 1);
         s2.buf.zero();
@@ -218,16 +233,17 @@ inline OneNormEst onenormest_power(kr_ctx* ctx, const kr_matrix* M, double scale
         nprod += 1;
         s2.buf.download(hz.data(), hz.size());
         int64_t jmax = 0;
-        double zmax = 0.0, zx = 0.0;
+        double zmax = -1.0;
         for (int64_t i = 0; i < n; ++i) {
-            double a = std::abs(hz[i * PW]);
-            if (a > zmax) { zmax = a; jmax = i; }
-            zx += hz[i * PW] * hx[i * PW];
+            const double a = std::abs(hz[i * PW]);
+            if (a >= zmax) { zmax = a; jmax = i; }
         }
+        if (itn >= 2 && est_j >= 0 && zmax == std::abs(hz[est_j * PW])) break;
         bool seen = false;
-        for (int v : hist) seen = seen || (v == (int)jmax);
-        if (itn > 1 && (zmax <= zx || seen)) break;
-        hist.push_back((int)jmax);
+        for (int64_t v : hist) seen = seen || (v == jmax);
+        if (itn >= 2 && seen) break;
+        hist.push_back(jmax);
+        cur = jmax;
         std::fill(hx.begin(), hx.end(), 0.0);
         hx[jmax * PW] = 1.0;
         x.buf.upload(hx.data(), hx.size());

@@ -59,28 +59,46 @@ def _onenormest_power(A, m):
             x = AT @ x
         return np.asarray(x).ravel()
 
+    # Higham & Tisseur (2000), Algorithm 2.4, as MathWorks' normest1.m states it for t = 1 column: the estimate,
+    # then the test on the estimate, then the PARALLEL-SIGN test (before the transposed product, which it saves),
+    # then the test on max|z| against the entry of the unit vector in use, ties of max|z| to the LAST index
+    # (normest1 reverses an ascending sort).  Pinned by tests/golden/reference_golden.json (A0_loops_*).
     x = np.ones(n) / n
     nprod = 0
     est_old = 0.0
-    ind_hist = set()
-    w = None
-    for itn in range(1, 6):
+    ind_hist = []
+    est_j = -1
+    cur = -1
+    s = np.zeros(n)
+    it = 0
+    while True:
+        it += 1
         y = fwd(x)
         nprod += 1
         est = float(np.abs(y).sum())
-        if itn > 1 and est <= est_old:
+        if est > est_old or it == 2:
+            est_j = cur
+        if it >= 2 and est <= est_old:
             est = est_old
             break
         est_old = est
-        w = y
+        if it > 5:
+            break
+        s_old = s
         s = np.sign(y)
         s[s == 0] = 1.0
+        if abs(float(s_old @ s)) == n:
+            break
         z = bwd(s)
         nprod += 1
-        jmax = int(np.argmax(np.abs(z)))
-        if itn > 1 and (np.abs(z).max() <= z @ x or jmax in ind_hist):
+        h = np.abs(z)
+        if it >= 2 and h.max() == h[est_j]:
             break
-        ind_hist.add(jmax)
+        jmax = int(np.argsort(h, kind="stable")[-1])
+        if it >= 2 and jmax in ind_hist:
+            break
+        ind_hist.append(jmax)
+        cur = jmax
         x = np.zeros(n)
         x[jmax] = 1.0
     return est_old, nprod

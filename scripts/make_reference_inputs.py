@@ -46,6 +46,21 @@ def build_inputs():
     out["Mexico_tol"] = 1e-9
     # probes for mc_trace(A0, n, 1e-3, 60, 1): K = ceil(60/30) = 2 iterations, S then G each (mc_trace.m:43-44)
     out["A0_probes"] = np.sign(rng.standard_normal((n0, 40)))
+    # ---- second batch (drawn AFTER everything above, so the first batch is unchanged)
+    # trace_exp(A0) = mc_trace(Afun, n, 1e-4, 1000, 1): K = ceil(1000/30) = 34 iterations at most, 20 probe columns each
+    out["A0_probes_long"] = np.sign(rng.standard_normal((n0, 680)))
+    hubs = np.argsort(-c0, kind="stable")
+    out["A0_self_node"] = float(hubs[2] + 1)
+    out["A0_set_edges"] = O.find_top_edges(A0, c0, 40, "min")[[0, 7, 19, 33]].astype(np.float64)
+    mixed = O.find_top_edges(A0, c0, 6, "mult").astype(np.float64)
+    mixed[1] = [hubs[0] + 1, hubs[0] + 1]                       # a self loop among the candidates (krylov_miobi.m:88-99)
+    out["A0_mixed_edges"] = mixed
+    out["A0_loop_nodes"] = np.sort(rng.choice(n0, 10, replace=False) + 1).astype(np.float64).reshape(-1, 1)
+    # weighted-experiment shapes on the Mexican grid (Tests/test_weighted_*: Omega = modifiable edges, X = weights)
+    T = sp.tril(Mx, -1).tocoo()
+    pick = np.sort(rng.choice(T.nnz, 6, replace=False))
+    out["Mexico_Omega"] = np.stack([T.row[pick] + 1, T.col[pick] + 1], 1).astype(np.float64)
+    out["Mexico_X"] = (0.1 * rng.uniform(0.0, 1.0, 6)).reshape(-1, 1)
     return out
 
 

@@ -1,11 +1,13 @@
-"""The route to PINNED parity.
+"""PINNED parity: oracle AND device against outputs of the reference's own sources.
 
-The reference is MATLAB-only and ships no golden vectors; this image has neither MATLAB nor Octave, so nothing here can
-run the reference.  scripts/make_reference_goldens.m runs the reference's OWN functions/*.m on the committed inputs
-tests/golden/reference_inputs.mat (made by scripts/make_reference_inputs.py) and writes
-tests/golden/reference_golden.json.  When that file is present these tests check the oracle (CPU tier) and the device
-path (GPU tier) against it at 1e-10 with equal iteration counts; until then they are skipped and parity stays
-"unpinned"."""
+The reference is MATLAB-only and ships no golden vectors.  tests/golden/reference_golden.json holds what the reference's
+UNMODIFIED functions/*.m produce on the committed inputs tests/golden/reference_inputs.mat (made by
+scripts/make_reference_inputs.py) when scripts/make_reference_goldens.m is executed - in this repository by the
+MATLAB-subset interpreter oracle/mlab (scripts/run_reference_goldens.py; provenance with the SHA-256 of every executed
+reference file in tests/golden/reference_golden.provenance.json), and by anyone with Octave / MATLAB the same script
+reproduces it.  These tests check the oracle (CPU tier) and the device path through the C ABI (GPU tier) against that
+file: 1e-10 relative (the documented exceptions carry their tolerance below), iteration counts, lucky flags,
+(s, m, mv, mvd, unA) and selected edges EQUAL."""
 import json
 import os
 import warnings
@@ -22,7 +24,9 @@ RTOL = 1e-10
 
 
 def inputs():
-    d = sio.loadmat(os.path.join(GOLDEN, "reference_inputs.mat"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d = sio.loadmat(os.path.join(GOLDEN, "reference_inputs.mat"))
     return {k: (sp.csr_matrix(v) if sp.issparse(v) else np.asarray(v)) for k, v in d.items() if not k.startswith("__")}
 
 
@@ -43,9 +47,28 @@ def test_reference_inputs_match_the_generator():
 def test_generator_script_calls_only_reference_functions():
     src = open(os.path.join(ROOT, "scripts", "make_reference_goldens.m")).read()
     for fn in ("trace_fun_update", "fun_update", "function_multiple_entries", "expmv", "normAm", "lanczos_krylov",
-               "mc_trace", "greedy_krylov"):
+               "arnoldi_krylov", "mc_trace", "trace_exp", "greedy_krylov", "krylov_miobi", "find_top_edges",
+               "find_top_missing_edges", "select_taylor_degree", "fun_and_grad_krylov_exp", "fun_and_grad_krylov_fun",
+               "hessianfcn_exp", "hessianfcn_fun", "multiple_frechet_eval", "edge2low_rank"):
         assert fn + "(" in src
     assert "addpath(fullfile(refdir, 'functions'))" in src
+
+
+def test_golden_file_is_present_with_provenance():
+    """Parity is pinned only while the golden file and the record of how it was made are both committed."""
+    ref = json.load(open(REF))
+    prov = json.load(open(os.path.join(GOLDEN, "reference_golden.provenance.json")))
+    assert len(ref) >= 55
+    ran = prov["reference_function_calls"]
+    for fn in ("trace_fun_update", "fun_update", "lanczos_krylov", "poly_krylov", "function_multiple_entries", "expmv",
+               "select_taylor_degree", "normAm", "afun_power", "mc_trace", "trace_exp", "krylov_miobi", "greedy_krylov",
+               "find_top_edges", "find_top_missing_edges", "multiple_frechet_eval", "hessianfcn_exp", "hessianfcn_fun",
+               "fun_and_grad_krylov_exp", "fun_and_grad_krylov_fun", "edge2low_rank"):
+        assert ran.get(fn, 0) >= 1, fn
+    assert all(f.startswith("functions/") and len(h) == 64 for f, h in prov["reference_files_executed"].items())
+    # a fact about the reference that only executing it shows: the three-output (Lanczos) form of fun_update ends in
+    # an index error at fun_update.m:137 (`Um(:, 1:size(Xm, 1))` on the two-block window)
+    assert ref["Mexico_lanczos_form_raises"] == [1]
 
 
 def _fun_update(P, A, U, B, fun, tol, it, basis):
@@ -56,62 +79,189 @@ def _fun_update(P, A, U, B, fun, tol, it, basis):
     return P.fun_update(A, U, B, fun, tol, it, 0, want_basis=basis)
 
 
-def _check(P, ref, A_of):
+class Checker:
+    def __init__(self, ref):
+        self.ref, self.bad, self.n = ref, [], 0
+
+    def close(self, name, got, key=None, rtol=RTOL, sl=None):
+        want = np.asarray(self.ref[key or name], dtype=np.float64)
+        if sl is not None:
+            want = want[sl]
+        got = np.asarray(got, dtype=np.float64).ravel(order="F")
+        self.n += 1
+        if got.shape != want.shape:
+            self.bad.append("%s: shape %s vs %s" % (name, got.shape, want.shape))
+            return
+        scale = np.max(np.abs(want)) if want.size else 1.0
+        err = np.max(np.abs(got - want)) / (scale if scale > 0 else 1.0) if want.size else 0.0
+        if not err <= rtol:
+            self.bad.append("%s: rel err %.3e > %.1e" % (name, err, rtol))
+
+    def equal(self, name, got, key=None, sl=None):
+        want = np.asarray(self.ref[key or name], dtype=np.float64)
+        if sl is not None:
+            want = want[sl]
+        got = np.asarray(got, dtype=np.float64).ravel(order="F")
+        self.n += 1
+        if got.shape != want.shape or not np.array_equal(got, want):
+            self.bad.append("%s: %s != %s" % (name, got.tolist()[:12], want.tolist()[:12]))
+
+
+def _check(P, ref, A_of, device):
     """P: the oracle module or the device package (same function names and argument order)."""
     I = inputs()
-    A0 = A_of(I["A0"])
-    n0 = I["A0"].shape[0]
+    C = Checker(ref)
+    A0raw = I["A0"]
+    A0 = A_of(A0raw)
+    n0 = A0raw.shape[0]
     tol0 = float(I["A0_tol"].ravel()[0])
+    c0 = I["A0_centrality"].ravel()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
+        # ---- trace_fun_update on candidate edges (a6), every shape the reference has
         for kind, sgn in (("break", -1.0), ("make", 1.0)):
             E = I["A0_%s_edges" % kind].astype(np.int64)
-            for h, (i, j) in enumerate(E):
-                U, B = edge_UB(n0, int(i), int(j), sgn)
-                x, it, lk = P.trace_fun_update(A0, U, B, tol0, 100, 0, "exp")
-                assert it == ref["A0_%s_iter" % kind][h] and bool(lk) == bool(ref["A0_%s_lucky" % kind][h])
-                assert abs(x - ref["A0_%s_x" % kind][h]) <= RTOL * abs(ref["A0_%s_x" % kind][h])
+            r = [P.trace_fun_update(A0, *edge_UB(n0, int(i), int(j), sgn), tol0, 100, 0, "exp") for i, j in E]
+            C.close("A0_%s_x" % kind, [v[0] for v in r])
+            C.equal("A0_%s_iter" % kind, [v[1] for v in r])
+            C.equal("A0_%s_lucky" % kind, [float(bool(v[2])) for v in r])
         Rome = A_of(I["Rome"])
-        for h, (i, j) in enumerate(I["Rome_edges"].astype(np.int64)):
-            U, B = edge_UB(I["Rome"].shape[0], int(i), int(j), -1.0)
-            x, it, _ = P.trace_fun_update(Rome, U, B, float(I["Rome_tol"].ravel()[0]), 100, 0, "sinh")
-            assert it == ref["Rome_sinh_iter"][h] and abs(x - ref["Rome_sinh_x"][h]) <= RTOL * abs(ref["Rome_sinh_x"][h])
+        nR = I["Rome"].shape[0]
+        for fun in ("sinh", "cosh"):
+            tolR = float(I["Rome_tol"].ravel()[0])
+            r = [P.trace_fun_update(Rome, *edge_UB(nR, int(i), int(j), -1.0), tolR, 100, 0, fun)
+                 for i, j in I["Rome_edges"].astype(np.int64)]
+            C.close("Rome_%s_x" % fun, [v[0] for v in r])
+            C.equal("Rome_%s_iter" % fun, [v[1] for v in r])
+        i_self = int(I["A0_self_node"].ravel()[0])
+        x, it, lk = P.trace_fun_update(A0, *edge_UB(n0, i_self, i_self, -1.0), tol0, 100, 0, "exp")
+        C.close("A0_selfloop value", [x], "A0_selfloop", sl=slice(0, 1))
+        C.equal("A0_selfloop iter, lucky", [it, float(bool(lk))], "A0_selfloop", sl=slice(1, 3))
+        As = A_of(sp.csr_matrix(A0raw[:100, :100]))
+        x, it, lk = P.trace_fun_update(As, *edge_UB(100, 3, 7, 1.0), 1e-8, 100, 0, "exp")
+        C.close("A0_dense_branch value", [x], "A0_dense_branch", sl=slice(0, 1))
+        C.equal("A0_dense_branch iter, lucky", [it, float(bool(lk))], "A0_dense_branch", sl=slice(1, 3))
+        Us, Bs = P.edge2low_rank(I["A0_set_edges"].astype(np.int64), n0)
+        Us = Us.toarray() if sp.issparse(Us) else np.asarray(Us)
+        C.equal("A0_edge_set_rk", [Us.shape[1]])
+        x, it, lk = P.trace_fun_update(A0, Us, Bs, tol0, 100, 0, "exp")
+        C.close("A0_edge_set value", [x], "A0_edge_set", sl=slice(0, 1))
+        C.equal("A0_edge_set iter, lucky", [it, float(bool(lk))], "A0_edge_set", sl=slice(1, 3))
+        # ---- fun_update, four-output (Arnoldi) form (a7); the three-output form of the reference raises
         Mx = A_of(I["Mexico"])
         tolM = float(I["Mexico_tol"].ravel()[0])
-        Xm, it3, _ = _fun_update(P, Mx, I["Mexico_U"], I["Mexico_B"], "exp", tolM, 100, False)[:3]
-        assert it3 == ref["Mexico_lanczos_iter"][0] and Xm.shape[0] == ref["Mexico_lanczos_dim"][0]
-        assert abs(np.trace(Xm) - ref["Mexico_lanczos_trace"][0]) <= RTOL * abs(ref["Mexico_lanczos_trace"][0])
-        Xm, it4, _, Um = _fun_update(P, Mx, I["Mexico_U"], I["Mexico_B"], "exp", tolM, 100, True)[:4]
-        assert it4 == ref["Mexico_arnoldi_iter"][0]
-        d = np.einsum("ij,jk,ik->i", Um, Xm, Um)
-        assert np.max(np.abs(d - np.asarray(ref["Mexico_arnoldi_update_diag"]))) <= RTOL * np.max(np.abs(ref["Mexico_arnoldi_update_diag"]))
+        for fun, key in (("exp", "Mexico_arnoldi"), ("sinh", "Mexico_arnoldi_sinh")):
+            Xm, it4, _, Um = _fun_update(P, Mx, I["Mexico_U"], I["Mexico_B"], fun, tolM, 100, True)[:4]
+            C.equal(key + "_iter", [it4])
+            if key + "_dim" in ref:
+                C.equal(key + "_dim", [Xm.shape[0]])
+            C.close(key + "_update_diag", np.einsum("ij,jk,ik->i", Um, Xm, Um))
+        # ---- L1: Ritz values of the projections after 4 block steps (basis-independent invariants)
+        V, H, p = P.lanczos_krylov(A0, I["A0_b"])[:3]
+        for _ in range(3):
+            V, H, p = P.lanczos_krylov(V, H, p)[:3]
+        G = np.asarray(H)[:-3, :]
+        C.close("A0_lanczos_ritz", np.sort(np.linalg.eigvalsh((G + G.T) / 2)))
+        V, K, H, p = P.arnoldi_krylov(A0, I["A0_b"])[:4]
+        for _ in range(3):
+            V, K, H, p = P.arnoldi_krylov(V, K, H, p)[:4]
+        V, K, H = np.asarray(V), np.asarray(K), np.asarray(H)
+        G = H[:-3, :]
+        C.close("A0_arnoldi_ritz", np.sort(np.linalg.eigvalsh((G + G.T) / 2)))
+        C.equal("A0_arnoldi_dims", list(V.shape) + list(H.shape) + list(K.shape))
+        # ---- entries of f(A) (a9)
         nrm = P.normest(A0, 1e-6)
         nrm = float(nrm[0] if isinstance(nrm, tuple) else nrm)
         X, itE = P.function_multiple_entries(A0, I["A0_omega"].astype(np.int64), "exp", 1e-10 * np.exp(nrm), 100)
-        assert itE == ref["A0_entries_iter"][0]
-        assert np.max(np.abs(X - np.asarray(ref["A0_entries"]))) <= RTOL * np.max(np.abs(ref["A0_entries"]))
+        C.equal("A0_entries_iter", [itE])
+        C.close("A0_entries", X)
+        nrm2 = P.normest(A0, 1e-2)
+        C.close("A0_normest", [float(nrm2[0] if isinstance(nrm2, tuple) else nrm2)])
+        # ---- expmv family (a11-a15)
         f, s, m, mv, mvd, unA = P.expmv(1, A0, I["A0_b"])
-        assert [s, m, mv, mvd, unA] == [int(v) for v in ref["A0_expmv_info"]]
-        assert np.max(np.abs(f.ravel(order="F") - np.asarray(ref["A0_expmv_f"]))) <= RTOL * np.max(np.abs(ref["A0_expmv_f"]))
+        C.equal("A0_expmv_info", [s, m, mv, mvd, unA])
+        C.close("A0_expmv_f", f)
+        f, s, m, mv, mvd, unA = P.expmv(0.5, A0, I["A0_b"], None, "double", True, False, True)
+        C.equal("A0_expmv_half_full_term_info", [s, m, mv, mvd, unA])
+        C.close("A0_expmv_half_full_term_f", f)
+        M, mvs, alpha, unA = P.select_taylor_degree(A0, I["A0_b"], 55, 8, "double", True, False)
+        C.equal("A0_std_info", [mvs, unA])
+        C.close("A0_std_alpha", alpha, rtol=1e-12)
+        Mr = np.asarray(ref["A0_std_M"]).reshape(55, 7, order="F")
+        M = np.asarray(M)
+        ok = M.shape == Mr.shape and np.all(np.abs(M - Mr) <= 1e-12 * np.abs(Mr))
+        C.n += 1
+        if not ok:
+            C.bad.append("A0_std_M differs")
         c9, mv9 = P.normAm(A0, 9)
-        assert mv9 == ref["A0_normAm9"][1] and abs(c9 - ref["A0_normAm9"][0]) <= 1e-12 * ref["A0_normAm9"][0]
+        C.equal("A0_normAm9 products", [mv9], "A0_normAm9", sl=slice(1, 2))
+        C.close("A0_normAm9 value", [c9], "A0_normAm9", sl=slice(0, 1), rtol=1e-12)
+        # the normest1 branch: self loops + shift give negative diagonal entries (normAm.m:24-26, nested afun_power)
+        loops = I["A0_loop_nodes"].ravel().astype(np.int64) - 1
+        Alraw = (A0raw + sp.csr_matrix((np.ones(loops.size), (loops, loops)), shape=(n0, n0))).tocsr()
+        Al = A_of(Alraw)
+        f, s, m, mv, mvd, unA = P.expmv(1, Al, I["A0_b"])
+        C.equal("A0_loops_expmv_info", [s, m, mv, mvd, unA])
+        C.close("A0_loops_expmv_f", f)
+        mu = Alraw.diagonal().sum() / n0
+        c5, mv5 = P.normAm(A_of((Alraw - mu * sp.identity(n0, format="csr")).tocsr()), 5)
+        C.equal("A0_loops_normAm5 products", [mv5], "A0_loops_normAm5", sl=slice(1, 2))
+        C.close("A0_loops_normAm5 value", [c5], "A0_loops_normAm5", sl=slice(0, 1), rtol=1e-12)
+        # ---- mc_trace / trace_exp with the replayed probes (a10, a14)
         pr = I["A0_probes"]
         tr, res, itm = P.mc_trace(A0, n0, 1e-3, 60, 1, 0, probes=[(pr[:, :10], pr[:, 10:20]), (pr[:, 20:30], pr[:, 30:40])])
-        assert itm == ref["A0_mc_trace"][2] and abs(tr - ref["A0_mc_trace"][0]) <= RTOL * abs(ref["A0_mc_trace"][0])
-        edges, rob, _ = P.greedy_krylov(I["A0"], 5, 50, I["A0_centrality"].ravel(), "min", tol0, 100, np.inf, 0, "break")
-        assert np.array_equal(np.asarray(edges).ravel(order="F"), np.asarray(ref["A0_greedy_edges"]).astype(np.int64))
-        assert abs(rob - ref["A0_greedy_rob"][0]) <= RTOL * abs(ref["A0_greedy_rob"][0])
+        C.equal("A0_mc_trace it", [itm], "A0_mc_trace", sl=slice(2, 3))
+        C.close("A0_mc_trace tr, res", [tr, res], "A0_mc_trace", sl=slice(0, 2))
+        pl = I["A0_probes_long"]
+        used = int(ref["A0_trace_exp"][1])
+        pairs = [(pl[:, 20 * k:20 * k + 10], pl[:, 20 * k + 10:20 * k + 20]) for k in range(34)]
+        C.close("A0_trace_exp", [P.trace_exp(A0, pairs)], sl=slice(0, 1))
+        assert used % 20 == 0 and used <= 680
+        # ---- candidate generators (f2) and the greedy drivers (f1)
+        for order in ("min", "mult"):
+            C.equal("A0_top_edges_" + order, np.asarray(P.find_top_edges(A0raw, c0, 30, order)))
+            C.equal("A0_top_missing_" + order, np.asarray(P.find_top_missing_edges(A0raw, c0, 30, order)))
+        edges, rob, _ = P.greedy_krylov(A0raw, 5, 50, c0, "min", tol0, 100, np.inf, 0, "break")
+        C.equal("A0_greedy_edges", np.asarray(edges))
+        C.close("A0_greedy_rob", [rob])
+        edges, rob, _ = P.greedy_krylov(A0raw, 3, 30, c0, "min", tol0, 100, np.inf, 0, "make")
+        C.equal("A0_greedy_make_edges", np.asarray(edges))
+        C.close("A0_greedy_make_rob", [rob])
+        edges, rob, Anew = P.krylov_miobi(A0raw, 2, I["A0_mixed_edges"].astype(np.int64), tol0, 100, np.inf, 0, "break", 2.0)
+        C.equal("A0_miobi_rescale_edges", np.asarray(edges))
+        C.close("A0_miobi_rescale_rob", [rob])
+        Anew = sp.csr_matrix(Anew.to_scipy() if hasattr(Anew, "to_scipy") else Anew)
+        Anew.eliminate_zeros()
+        C.equal("A0_miobi_rescale_nnz", [Anew.nnz])
+        # ---- weighted experiments: callbacks (a8) and exact Hessians (f3)
+        Om = I["Mexico_Omega"].astype(np.int64)
+        Xw = I["Mexico_X"].ravel()
+        nM = float(P.normest(Mx, 1e-6)[0]) if isinstance(P.normest(Mx, 1e-6), tuple) else float(P.normest(Mx, 1e-6))
+        eA, _ = P.function_multiple_entries(Mx, Om, "exp", 1e-10 * np.exp(nM), 100)
+        C.close("Mexico_eA", eA)
+        fv, gr = P.fun_and_grad_krylov_exp(Xw, Mx, Om, np.asarray(ref["Mexico_eA"]), 1e-10, 100, 0)
+        C.close("Mexico_fg_exp", np.concatenate([[fv], np.ravel(gr)]))
+        fv, gr = P.fun_and_grad_krylov_exp(0 * Xw, Mx, Om, np.asarray(ref["Mexico_eA"]), 1e-10, 100, 0)
+        C.close("Mexico_fg_exp_at_zero", np.concatenate([[fv], np.ravel(gr)]))
+        dfA, _ = P.function_multiple_entries(Mx, Om, "cosh", 1e-10 * np.cosh(nM), 100)
+        C.close("Mexico_dfA_cosh", dfA)
+        fv, gr = P.fun_and_grad_krylov_fun(Xw, Mx, Om, "sinh", "cosh", np.asarray(ref["Mexico_dfA_cosh"]), 1e-10, 100, 0)
+        C.close("Mexico_fg_sinh", np.concatenate([[fv], np.ravel(gr)]))
+        C.close("Mexico_hessian_exp", P.hessianfcn_exp(Xw, I["Mexico"], Om, 1e-10, 100))
+        C.close("Mexico_hessian_sinh", P.hessianfcn_fun(Xw, I["Mexico"], Om, "sinh", 1e-10, 100))
+        if hasattr(P, "multiple_frechet_eval"):
+            out = P.multiple_frechet_eval(I["Mexico"], Om, "exp", 1e-10, 100, np.inf, 0)
+            C.equal("Mexico_frechet_iter", [out[-1]])
+    assert not C.bad, "%d of %d checks against the reference's outputs failed:\n  %s" % (len(C.bad), C.n, "\n  ".join(C.bad))
+    return C.n
 
 
-@pytest.mark.skipif(not os.path.exists(REF), reason="tests/golden/reference_golden.json absent: run "
-                    "scripts/make_reference_goldens.m under Octave/MATLAB against the reference (parity unpinned until then)")
 def test_oracle_matches_reference_goldens():
     import oracle as O
-    _check(O, json.load(open(REF)), lambda A: A)
+    assert _check(O, json.load(open(REF)), lambda A: A, device=False) >= 60
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.path.exists(REF), reason="tests/golden/reference_golden.json absent (see above)")
 def test_device_matches_reference_goldens():
     import krylov_robustness_b200 as kr
-    _check(kr, json.load(open(REF)), lambda A: kr.Matrix(A))
+    assert _check(kr, json.load(open(REF)), lambda A: kr.Matrix(A), device=True) >= 60
