@@ -9,12 +9,15 @@ under ``functions/`` (each function's docstring cites the file:line it follows).
 is pure MATLAB and neither MATLAB nor GNU Octave exists in this image, so the reference itself
 cannot be executed here.
 
-PARITY UNPINNED: the reference ships no golden vectors, no assertions and no expected-value
-files.  The only pins available are the dense identities the reference
-keeps in its ``debug`` branches (``trace_fun_update.m:91-102``, ``fun_and_grad_krylov_exp.m:90-111``,
-``function_multiple_entries.m:80-82``) - tests/test_oracle_*.py turn those into assertions against
-dense ``eigh``/``expm`` ground truth on the reference's own graphs.  MATLAB built-ins with no
-source (qr, eig, expm, funm, normest, eigs) are replaced by their LAPACK / SciPy equivalents.
+PARITY PINNED (round 2): ``oracle/mlab`` is a from-scratch interpreter for the MATLAB subset the reference is
+written in; ``scripts/run_reference_goldens.py`` executes the reference's UNMODIFIED ``functions/*.m`` with it (driven
+by ``scripts/make_reference_goldens.m``) and the outputs are committed as ``tests/golden/reference_golden.json`` with
+their provenance (SHA-256 of every reference file executed).  ``tests/test_reference_goldens.py`` holds this package
+and the device path to those outputs: 1e-10 relative, iteration counts / flags / selected edges equal.  MATLAB's
+closed-source built-ins are LAPACK / SciPy stand-ins there as here (``oracle/mlab/__init__.py`` says what that means).
+The dense identities the reference keeps in its ``debug`` branches (``trace_fun_update.m:91-102``,
+``fun_and_grad_krylov_exp.m:90-111``, ``function_multiple_entries.m:80-82``) remain as a second, independent pin:
+tests/test_oracle_*.py turn them into assertions against dense ``eigh``/``expm`` ground truth on the reference's graphs.
 """
 from .theta import THETA
 from .krylov import lanczos_krylov, arnoldi_krylov

@@ -2,7 +2,8 @@
 
 CPU part: the oracle reproduces its own pinned outputs (guards against drift of the checker).
 GPU part: the device path hits the same numbers through the C ABI without re-running the oracle.
-The reference itself ships no golden vectors (parity unpinned, see oracle/__init__.py)."""
+The reference itself ships no golden vectors; outputs of the reference's own sources are pinned separately in
+tests/test_reference_goldens.py (tests/golden/reference_golden.json)."""
 import json
 import os
 import warnings
