@@ -31,11 +31,23 @@ def edge2low_rank(E, n, sign=-1.0):
 
 
 def compute_centrality(A, kind="eig"):
-    """c = compute_centrality(A,type)  (compute_centrality.m:15-19 'eig', :18-19 'deg')."""
+    """c = compute_centrality(A,type)  (compute_centrality.m:9-10 'exp', :15-17 'eig', :18-19 'deg', :20-26 'pr';
+    'res' (:11-14) uses an undefined variable in the reference and is not restated)."""
     if kind == "deg":
         return np.asarray(A.sum(axis=0)).ravel()
     n = A.shape[0]
-    _, u = spla.eigsh(sp.csr_matrix(A).astype(np.float64), k=1, which="LM", v0=np.ones(n), tol=1e-12)
+    A = sp.csr_matrix(A).astype(np.float64)
+    if kind == "exp":
+        import scipy.linalg as sla
+        return np.diag(sla.expm(A.toarray())).copy()
+    if kind == "pr":
+        alpha = 0.85
+        dinv = 1.0 / np.asarray(A.sum(axis=0)).ravel()
+        op = spla.LinearOperator((n, n), dtype=np.float64,
+                                 matvec=lambda x: alpha * (A @ (dinv * np.ravel(x))) + (1 - alpha) * np.sum(x) / n * np.ones(n))
+        _, u = spla.eigs(op, k=1, which="LM", v0=np.ones(n), tol=0)
+        return np.abs(u[:, 0])
+    _, u = spla.eigsh(A, k=1, which="LM", v0=np.ones(n), tol=1e-12)
     return np.abs(u[:, 0])
 
 

@@ -1271,3 +1271,32 @@ def _cellfun(I, a, n):
 @builtin("balance")
 def _balance(I, a, n):
     raise MatlabError("balance is not available (bal = true is never used on this path)")
+
+
+@builtin("eigs")
+def _eigs(I, a, n):
+    """eigs(A, k) / eigs(Afun, n, k): the k = 1 eigenpair of largest magnitude (ARPACK, as in MATLAB).  The sign of
+    the vector is arbitrary on both sides; compute_centrality.m takes abs()."""
+    import scipy.sparse.linalg as spla
+    if isinstance(a[0], FH):
+        nn = to_int(a[1])
+        k = to_int(a[2]) if len(a) > 2 else 6
+        op = spla.LinearOperator((nn, nn), matvec=lambda x: dense(I.call_handle(a[0], [np.asarray(x, dtype=np.float64).reshape(-1, 1)], 1)[0]).reshape(-1),
+                                 dtype=np.float64)
+        w, V = spla.eigs(op, k=k, which="LM", v0=np.ones(nn), tol=0)
+        if np.all(np.abs(w.imag) <= 1e-14 * np.abs(w)) and np.all(np.abs(V.imag) <= 1e-12):
+            w, V = w.real, V.real
+    else:
+        A = a[0]
+        k = to_int(a[1]) if len(a) > 1 else 6
+        A = sp.csc_matrix(A).astype(np.float64)
+        sym = (A != A.T).nnz == 0
+        if sym:
+            w, V = spla.eigsh(A, k=k, which="LM", v0=np.ones(A.shape[0]), tol=0)
+        else:
+            w, V = spla.eigs(A, k=k, which="LM", v0=np.ones(A.shape[0]), tol=0)
+    order = np.argsort(-np.abs(w), kind="stable")
+    w, V = w[order], V[:, order]
+    if n <= 1:
+        return w.reshape(-1, 1)
+    return V, np.diag(w)

@@ -162,6 +162,12 @@ out.Mexico_hessian_sinh = Hes(:);
 [Umf, Xmf, Vmf, rowf, colf, itf] = multiple_frechet_eval(in.Mexico, in.Mexico_Omega, @exp, 1e-10, 100, inf, 0);
 out.Mexico_frechet_iter = itf;
 
+% ---- compute_centrality (eigs is ARPACK here as in MATLAB; the vector's sign is arbitrary, the reference takes abs)
+out.A0_centrality_eig = compute_centrality(in.A0, 'eig');
+out.A0_centrality_deg = full(compute_centrality(in.A0, 'deg'));
+out.A0_centrality_pr = compute_centrality(in.A0, 'pr');
+out.A0_centrality_exp = full(compute_centrality(in.A0, 'exp'));
+
 % ---- JSON by hand (jsonencode is missing from older Octave)
 if ~exist('golden_path', 'var'), golden_path = fullfile(root, 'tests', 'golden', 'reference_golden.json'); end
 fid = fopen(golden_path, 'w');

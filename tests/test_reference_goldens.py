@@ -58,7 +58,7 @@ def test_golden_file_is_present_with_provenance():
     """Parity is pinned only while the golden file and the record of how it was made are both committed."""
     ref = json.load(open(REF))
     prov = json.load(open(os.path.join(GOLDEN, "reference_golden.provenance.json")))
-    assert len(ref) >= 55
+    assert len(ref) >= 62
     ran = prov["reference_function_calls"]
     for fn in ("trace_fun_update", "fun_update", "lanczos_krylov", "poly_krylov", "function_multiple_entries", "expmv",
                "select_taylor_degree", "normAm", "afun_power", "mc_trace", "trace_exp", "krylov_miobi", "greedy_krylov",
@@ -233,6 +233,14 @@ def _check(P, ref, A_of, device):
         Anew = sp.csr_matrix(Anew.to_scipy() if hasattr(Anew, "to_scipy") else Anew)
         Anew.eliminate_zeros()
         C.equal("A0_miobi_rescale_nnz", [Anew.nnz])
+        # ---- compute_centrality (f2).  The reference calls eigs (ARPACK, residual ~1e-15); the device runs a power
+        #      iteration to tol 1e-13 on the iterate and 'exp' a Krylov approximation of diag(expm(A)) instead of the
+        #      dense expm: 1e-8 of the largest entry, which is far below the gaps that order the candidate lists
+        #      (the lists themselves are compared exactly above)
+        ctol = 1e-8 if device else 1e-12
+        for kind in ("eig", "deg", "pr", "exp"):
+            C.close("A0_centrality_" + kind, np.asarray(P.compute_centrality(A0raw, kind)).ravel(),
+                    rtol=0.0 if kind == "deg" else ctol)
         # ---- weighted experiments: callbacks (a8) and exact Hessians (f3)
         Om = I["Mexico_Omega"].astype(np.int64)
         Xw = I["Mexico_X"].ravel()
@@ -258,10 +266,10 @@ def _check(P, ref, A_of, device):
 
 def test_oracle_matches_reference_goldens():
     import oracle as O
-    assert _check(O, json.load(open(REF)), lambda A: A, device=False) >= 60
+    assert _check(O, json.load(open(REF)), lambda A: A, device=False) >= 67
 
 
 @pytest.mark.gpu
 def test_device_matches_reference_goldens():
     import krylov_robustness_b200 as kr
-    assert _check(kr, json.load(open(REF)), lambda A: kr.Matrix(A), device=True) >= 60
+    assert _check(kr, json.load(open(REF)), lambda A: kr.Matrix(A), device=True) >= 67
