@@ -992,7 +992,11 @@ def _error(I, a, n):
         raise MatlabError("error")
     msg = a[0]
     if len(a) > 1:
-        msg = _sprintf(a[0], a[1:])
+        import re
+        if re.fullmatch(r"\w+(:\w+)+", a[0]):          # error('pkg:id', 'format', ...)
+            msg = _sprintf(a[1], a[2:])
+        else:
+            msg = _sprintf(a[0], a[1:])
     raise MatlabError(msg)
 
 

@@ -46,7 +46,7 @@ class Interpreter:
     def __init__(self, path=(), stdout=None):
         from . import builtins as B
         self.path = [os.path.abspath(p) for p in path]
-        self.builtins = B.TABLE
+        self.builtins = dict(B.TABLE)  # per instance: a host may add functions (tests/mex_stub/bridge.py: kr_mex)
         self.cache = {}               # file -> (script_body, {name: Function})
         self.lookup_cache = {}
         self.globals = {}

@@ -9,11 +9,16 @@
 % file at 1e-10 with equal iteration counts.  Only built-ins that Octave has are used (no table/graph/funm: the cases
 % below use @exp, for which the reference calls expm).  mc_trace draws its probes from randn (mc_trace.m:43-44,
 % unseeded); a shim randn.m placed first on the path replays the committed probe blocks instead.
-if ~exist('refdir', 'var'), error('set refdir to a checkout of COMPiLELab/krylov_robustness'); end
+% Drop-in mode: with `dropin_dir` set (to krylov_robustness_b200/matlab) the SAME calls go through this repository's
+% wrappers -> MEX gateway -> CUDA instead, and the sections that need reference files without a wrapper (greedy_krylov,
+% find_top_*, edge2low_rank, compute_centrality, multiple_frechet_eval: host glue above the path) are skipped;
+% tests/test_gpu_dropin_matlab.py compares what comes out with the reference's numbers.
+dropin = exist('dropin_dir', 'var');
+if ~dropin && ~exist('refdir', 'var'), error('set refdir to a checkout of COMPiLELab/krylov_robustness'); end
 here = fileparts(mfilename('fullpath'));
 root = fileparts(here);
 in = load(fullfile(root, 'tests', 'golden', 'reference_inputs.mat'));
-addpath(fullfile(refdir, 'functions'));
+if dropin, addpath(dropin_dir); else, addpath(fullfile(refdir, 'functions')); end
 out = struct();
 
 % ---- trace_fun_update on candidate edges (functions/krylov_miobi.m:76-99 call shape)
@@ -79,8 +84,10 @@ rmpath(shim);
 out.A0_mc_trace = [tr res itm];
 
 % ---- greedy_krylov: 5 rounds, Q = 50 (Tests/test_unweighted_break.m:74 call shape, smaller)
-[edges, rob] = greedy_krylov(in.A0, 5, 50, in.A0_centrality, 'min', in.A0_tol, 100, inf, 0, 'break');
-out.A0_greedy_edges = edges(:); out.A0_greedy_rob = rob;
+if ~dropin
+    [edges, rob] = greedy_krylov(in.A0, 5, 50, in.A0_centrality, 'min', in.A0_tol, 100, inf, 0, 'break');
+    out.A0_greedy_edges = edges(:); out.A0_greedy_rob = rob;
+end
 
 % ==== second batch =========================================================================================
 % ---- trace_fun_update: self loop (rank one, krylov_miobi.m:88-99), dense branch n <= 130 (trace_fun_update.m:37-51),
@@ -92,7 +99,14 @@ As = in.A0(1:100, 1:100);
 U = zeros(100, 2); U(3, 1) = 1; U(7, 2) = 1;
 [xd, itd, lkd] = trace_fun_update(As, U, [0 1; 1 0], 1e-8, 100, 0);
 out.A0_dense_branch = [xd itd lkd];
-[Us, Bs] = edge2low_rank(in.A0_set_edges, n0);
+if ~dropin
+    [Us, Bs] = edge2low_rank(in.A0_set_edges, n0);
+else    % the same U, B written out (edge2low_rank.m:3-12) - the reference file is not on the drop-in path
+    ut = unique(in.A0_set_edges(:)); Us = sparse(ut, 1:length(ut), 1, n0, length(ut)); Bs = zeros(length(ut));
+    for q = 1:size(in.A0_set_edges, 1)
+        a1 = find(ut == in.A0_set_edges(q, 1)); a2 = find(ut == in.A0_set_edges(q, 2)); Bs(a1, a2) = -1; Bs(a2, a1) = -1;
+    end
+end
 [xe, ite, lke] = trace_fun_update(in.A0, full(Us), Bs, in.A0_tol, 100, 0);
 out.A0_edge_set = [xe ite lke]; out.A0_edge_set_rk = size(Us, 2);
 x = zeros(size(in.Rome_edges, 1), 1); it = x;
@@ -133,6 +147,7 @@ tre = trace_exp(in.A0);
 rmpath(shim);
 out.A0_trace_exp = [tre KR_PROBE_POS];
 
+if ~dropin
 % ---- candidate generators, both orderings
 E1 = find_top_edges(in.A0, in.A0_centrality, 30, 'min');  out.A0_top_edges_min = E1(:);
 E2 = find_top_edges(in.A0, in.A0_centrality, 30, 'mult'); out.A0_top_edges_mult = E2(:);
@@ -142,6 +157,7 @@ E4 = find_top_missing_edges(in.A0, in.A0_centrality, 30, 'mult'); out.A0_top_mis
 % ---- greedy 'make'; krylov_miobi on an explicit list with a self loop and rescale ~= 1 (krylov_miobi.m:78-99)
 [edges, rob] = greedy_krylov(in.A0, 3, 30, in.A0_centrality, 'min', in.A0_tol, 100, inf, 0, 'make');
 out.A0_greedy_make_edges = edges(:); out.A0_greedy_make_rob = rob;
+end
 [edges, rob, Anew] = krylov_miobi(in.A0, 2, in.A0_mixed_edges, in.A0_tol, 100, inf, 0, 'break', 2);
 out.A0_miobi_rescale_edges = edges(:); out.A0_miobi_rescale_rob = rob; out.A0_miobi_rescale_nnz = nnz(Anew);
 
@@ -159,14 +175,18 @@ Hes = hessianfcn_exp(in.Mexico_X, in.Mexico, in.Mexico_Omega, 1e-10, 100);
 out.Mexico_hessian_exp = Hes(:);
 Hes = hessianfcn_fun(in.Mexico_X, in.Mexico, in.Mexico_Omega, @sinh, 1e-10, 100);
 out.Mexico_hessian_sinh = Hes(:);
-[Umf, Xmf, Vmf, rowf, colf, itf] = multiple_frechet_eval(in.Mexico, in.Mexico_Omega, @exp, 1e-10, 100, inf, 0);
-out.Mexico_frechet_iter = itf;
+if ~dropin
+    [Umf, Xmf, Vmf, rowf, colf, itf] = multiple_frechet_eval(in.Mexico, in.Mexico_Omega, @exp, 1e-10, 100, inf, 0);
+    out.Mexico_frechet_iter = itf;
+end
 
+if ~dropin
 % ---- compute_centrality (eigs is ARPACK here as in MATLAB; the vector's sign is arbitrary, the reference takes abs)
 out.A0_centrality_eig = compute_centrality(in.A0, 'eig');
 out.A0_centrality_deg = full(compute_centrality(in.A0, 'deg'));
 out.A0_centrality_pr = compute_centrality(in.A0, 'pr');
 out.A0_centrality_exp = full(compute_centrality(in.A0, 'exp'));
+end
 
 % ---- JSON by hand (jsonencode is missing from older Octave)
 if ~exist('golden_path', 'var'), golden_path = fullfile(root, 'tests', 'golden', 'reference_golden.json'); end

@@ -49,6 +49,11 @@ void mxFree(void* p);
 void mexErrMsgTxt(const char* msg);
 void mexErrMsgIdAndTxt(const char* id, const char* fmt, ...);
 int mexAtExit(void (*fn)(void));
+int mxGetClassID(const mxArray* a);
+int mxIsLogical(const mxArray* a);
+int mxIsChar(const mxArray* a);
+/* not MEX API: entry for a host that wants gateway errors back as a message (see mex_stub.c) */
+int kr_stub_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[], char* err, size_t errlen);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 /* mex_stub.c - see mex.h: a few dozen lines of mxArray bookkeeping, test infrastructure only. */
 #include "mex.h"
+#include <setjmp.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -63,14 +64,37 @@ int mxGetString(const mxArray* a, char* buf, mwSize buflen) {
 }
 void* mxMalloc(size_t n) { return malloc(n ? n : 1); }
 void mxFree(void* p) { free(p); }
-void mexErrMsgTxt(const char* msg) { fprintf(stderr, "MEX error: %s\n", msg); exit(3); }
-void mexErrMsgIdAndTxt(const char* id, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    fprintf(stderr, "MEX error [%s]: ", id);
-    vfprintf(stderr, fmt, ap);
-    fprintf(stderr, "\n");
-    va_end(ap);
+/* Errors: a real MEX host unwinds to the interpreter.  The harness executable simply exits; a host that calls the
+ * gateway through kr_stub_call (the interpreter bridge, oracle/mlab/mexbridge.py) gets the message back instead. */
+static jmp_buf g_jmp;
+static int g_armed = 0;
+static char g_errmsg[1024];
+static void raise_error(void) {
+    if (g_armed) longjmp(g_jmp, 1);
+    fprintf(stderr, "MEX error: %s\n", g_errmsg);
     exit(3);
 }
+void mexErrMsgTxt(const char* msg) { snprintf(g_errmsg, sizeof g_errmsg, "%s", msg); raise_error(); }
+void mexErrMsgIdAndTxt(const char* id, const char* fmt, ...) {
+    va_list ap;
+    (void)id;
+    va_start(ap, fmt);
+    vsnprintf(g_errmsg, sizeof g_errmsg, fmt, ap);
+    va_end(ap);
+    raise_error();
+}
+int kr_stub_call(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[], char* err, size_t errlen) {
+    g_armed = 1;
+    if (setjmp(g_jmp)) {
+        g_armed = 0;
+        snprintf(err, errlen, "%s", g_errmsg);
+        return 1;
+    }
+    mexFunction(nlhs, plhs, nrhs, prhs);
+    g_armed = 0;
+    return 0;
+}
+int mxGetClassID(const mxArray* a) { return (int)a->cls; }
+int mxIsLogical(const mxArray* a) { return a->cls == mxLOGICAL_CLASS; }
+int mxIsChar(const mxArray* a) { return a->cls == mxCHAR_CLASS; }
 int mexAtExit(void (*fn)(void)) { return atexit(fn); }
