@@ -95,10 +95,13 @@ class MexHost:
             S = sp.csc_matrix(v).astype(np.float64)
             S.sort_indices()
             a = L.mxCreateSparse(S.shape[0], S.shape[1], max(S.nnz, 1), 0)
-            C.memmove(L.mxGetJc(a), S.indptr.astype(np.uint64).ctypes.data, (S.shape[1] + 1) * 8)
+            jc = np.ascontiguousarray(S.indptr, dtype=np.uint64)      # keep the temporaries alive across memmove
+            ir = np.ascontiguousarray(S.indices, dtype=np.uint64)
+            pr = np.ascontiguousarray(S.data, dtype=np.float64)
+            C.memmove(L.mxGetJc(a), jc.ctypes.data, (S.shape[1] + 1) * 8)
             if S.nnz:
-                C.memmove(L.mxGetIr(a), S.indices.astype(np.uint64).ctypes.data, S.nnz * 8)
-                C.memmove(L.mxGetPr(a), np.ascontiguousarray(S.data).ctypes.data, S.nnz * 8)
+                C.memmove(L.mxGetIr(a), ir.ctypes.data, S.nnz * 8)
+                C.memmove(L.mxGetPr(a), pr.ctypes.data, S.nnz * 8)
             return a
         v = np.asarray(v)
         if v.dtype == np.bool_ and v.size == 1:

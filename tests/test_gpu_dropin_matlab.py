@@ -59,6 +59,23 @@ def test_wrappers_parse_and_the_gateway_refuses_to_run_without_a_gpu(tmp_path):
     I.addpath(WRAPPERS)
     with pytest.raises(MatlabError):
         I.call("kr_mex", "no_such_operation", nargout=1)
+    # marshalling round trips (interpreter value -> mxArray -> interpreter value)
+    import scipy.sparse as sp
+    rng = np.random.default_rng(0)
+    S = sp.random(40, 30, 0.1, format="csc", random_state=1)
+    D = rng.standard_normal((7, 3))
+    for v in (S, D, D[:, :1].T, "sinh", np.array([[True]]), bridge.UInt64(2**40 + 5), np.zeros((0, 0))):
+        p = H.to_mx(v)
+        back = H.from_mx(p)
+        H.L.mxDestroyArray(p)
+        if sp.issparse(v):
+            assert (back != v).nnz == 0 and back.shape == v.shape
+        elif isinstance(v, bridge.UInt64):
+            assert back.v == v.v
+        elif isinstance(v, str):
+            assert back == v
+        else:
+            assert back.shape == np.atleast_2d(v).shape and np.array_equal(back, np.atleast_2d(v))
     import torch
     if not torch.cuda.is_available():
         import scipy.sparse as sp
