@@ -175,6 +175,13 @@ Hes = hessianfcn_exp(in.Mexico_X, in.Mexico, in.Mexico_Omega, 1e-10, 100);
 out.Mexico_hessian_exp = Hes(:);
 Hes = hessianfcn_fun(in.Mexico_X, in.Mexico, in.Mexico_Omega, @sinh, 1e-10, 100);
 out.Mexico_hessian_sinh = Hes(:);
+% 30 modifiable edges (Tests/test_weighted_sinh_lbfgs.m call shape): wide blocks, dense fall-back of fun_update.m:84-90
+dfA30 = function_multiple_entries(in.Mexico, in.Mexico_Omega30, @cosh, 1e-10 * cosh(normest(in.Mexico)), 100, inf, 0);
+[fv, gr] = fun_and_grad_krylov_fun(in.Mexico_X30, in.Mexico, in.Mexico_Omega30, @sinh, @cosh, dfA30, 1e-8, 100, 0);
+out.Mexico_fg30_sinh = [fv; gr]; out.Mexico_dfA30_cosh = dfA30;
+eA30 = function_multiple_entries(in.Mexico, in.Mexico_Omega30, @exp, tolE, 100, inf, 0);
+[fv, gr] = fun_and_grad_krylov_exp(in.Mexico_X30, in.Mexico, in.Mexico_Omega30, eA30, 1e-8, 100, 0);
+out.Mexico_fg30_exp = [fv; gr]; out.Mexico_eA30 = eA30;
 if ~dropin
     [Umf, Xmf, Vmf, rowf, colf, itf] = multiple_frechet_eval(in.Mexico, in.Mexico_Omega, @exp, 1e-10, 100, inf, 0);
     out.Mexico_frechet_iter = itf;

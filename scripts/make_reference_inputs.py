@@ -61,6 +61,11 @@ def build_inputs():
     pick = np.sort(rng.choice(T.nnz, 6, replace=False))
     out["Mexico_Omega"] = np.stack([T.row[pick] + 1, T.col[pick] + 1], 1).astype(np.float64)
     out["Mexico_X"] = (0.1 * rng.uniform(0.0, 1.0, 6)).reshape(-1, 1)
+    # ---- third batch: the call shape of Tests/test_weighted_*_lbfgs.m (30 modifiable edges -> a block of ~55 columns;
+    # on a 552-node grid the Krylov space saturates and fun_update.m:84-90 switches to dense arithmetic)
+    pick30 = np.sort(rng.choice(T.nnz, 30, replace=False))
+    out["Mexico_Omega30"] = np.stack([T.row[pick30] + 1, T.col[pick30] + 1], 1).astype(np.float64)
+    out["Mexico_X30"] = (0.1 * rng.uniform(0.0, 1.0, 30)).reshape(-1, 1)
     return out
 
 

@@ -25,22 +25,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(refdir, out_json=None):
+SCRIPTS = {False: ("make_reference_goldens.m", "reference_golden"), True: ("make_reference_goldens_c1.m", "reference_golden_c1")}
+
+
+def run(refdir, out_json=None, c1=False):
     """-> (golden dict, provenance dict).  The .m script writes the JSON itself; `out_json` redirects it."""
+    script, stem = SCRIPTS[c1]
     from oracle.mlab import Interpreter
     interp = Interpreter(stdout=io.StringIO())
     ws = {"refdir": refdir}
     if out_json is not None:
         ws["golden_path"] = out_json
     t0 = time.time()
-    interp.run_script(os.path.join(ROOT, "scripts", "make_reference_goldens.m"), ws)
-    path = out_json or os.path.join(ROOT, "tests", "golden", "reference_golden.json")
+    interp.run_script(os.path.join(ROOT, "scripts", script), ws)
+    path = out_json or os.path.join(ROOT, "tests", "golden", stem + ".json")
     golden = json.load(open(path))
     executed = sorted(f for f in interp.cache if os.path.abspath(f).startswith(os.path.abspath(refdir)))
     prov = {
         "engine": "oracle/mlab (MATLAB-subset interpreter of this repository) executing the reference's unmodified "
                   "functions/*.m; built-ins are NumPy/SciPy (LAPACK) stand-ins for MATLAB's closed-source ones",
-        "script": "scripts/make_reference_goldens.m",
+        "script": "scripts/" + script,
         "reference_files_executed": {os.path.relpath(f, refdir): hashlib.sha256(open(f, "rb").read()).hexdigest()
                                      for f in executed},
         "reference_function_calls": dict(sorted(interp.calls.items())),
@@ -54,23 +58,25 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--refdir", default="/root/reference")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--c1", action="store_true", help="the long BASELINE-C1 greedy runs (make_reference_goldens_c1.m, ~10 min)")
     a = ap.parse_args()
+    stem = SCRIPTS[a.c1][1]
     if not os.path.isdir(os.path.join(a.refdir, "functions")):
         sys.exit("no reference checkout at %s" % a.refdir)
-    gpath = os.path.join(ROOT, "tests", "golden", "reference_golden.json")
+    gpath = os.path.join(ROOT, "tests", "golden", stem + ".json")
     if a.check:
         import tempfile
         import numpy as np
         tmp = os.path.join(tempfile.mkdtemp(), "g.json")
-        fresh, _ = run(a.refdir, tmp)
+        fresh, _ = run(a.refdir, tmp, a.c1)
         stored = json.load(open(gpath))
         assert set(fresh) == set(stored), sorted(set(fresh) ^ set(stored))
         for k in fresh:
             assert np.array_equal(np.asarray(fresh[k]), np.asarray(stored[k])), k
-        print("reference_golden.json reproduced bit for bit (%d entries)" % len(fresh))
+        print("%s.json reproduced bit for bit (%d entries)" % (stem, len(fresh)))
         return
-    golden, prov = run(a.refdir)
-    with open(os.path.join(ROOT, "tests", "golden", "reference_golden.provenance.json"), "w") as fh:
+    golden, prov = run(a.refdir, None, a.c1)
+    with open(os.path.join(ROOT, "tests", "golden", stem + ".provenance.json"), "w") as fh:
         json.dump(prov, fh, indent=1)
         fh.write("\n")
     print("wrote %s (%d entries) in %.1f s; reference functions executed: %s"

@@ -114,6 +114,10 @@ def test_generator_script_through_the_wrappers_reproduces_the_reference(tmp_path
             continue
         if k == "A0_trace_exp":          # the wrapper draws all 34 probe pairs up front; the value is what counts
             w, g = w[:1], g[:1]
+        if k == "Mexico_fg30_sinh":      # objective from a ~55-column Lanczos block: see tests/test_reference_goldens.py
+            if not abs(g[0] - w[0]) <= 1e-3 * abs(w[0]):
+                bad.append("%s objective: %r vs %r" % (k, g[0], w[0]))
+            w, g = w[1:], g[1:]
         if k in MIXED:
             nv = MIXED[k]
             if not np.array_equal(w[nv:], g[nv:]):
