@@ -324,22 +324,55 @@ def test_oracle_reproduces_the_reference_c1_greedy_runs():
         assert abs(r - ref[key + "_rob"][0]) <= 1e-12 * abs(ref[key + "_rob"][0]), key
 
 
+def _twin_relabelling(A, got, want):
+    """A permutation pi of the nodes that only moves nodes WITHIN classes of identical neighbourhoods of A (any such pi
+    is an automorphism of the graph) and maps the edge sequence `got` onto `want` round by round, or None."""
+    A = sp.csr_matrix(A)
+    nb = [frozenset(A.indices[A.indptr[i]:A.indptr[i + 1]].tolist()) for i in range(A.shape[0])]
+    pi, inv = {}, {}
+
+    def bind(a, c):
+        if pi.get(a, c) != c or inv.get(c, a) != a or nb[a - 1] != nb[c - 1]:
+            return False
+        pi[a], inv[c] = c, a
+        return True
+
+    for (a, b), (c, d) in zip(got.astype(int).tolist(), want.astype(int).tolist()):
+        saved = (dict(pi), dict(inv))
+        if bind(a, c) and bind(b, d):
+            continue
+        pi, inv = dict(saved[0]), dict(saved[1])
+        if not (bind(a, d) and bind(b, c)):
+            return None
+    return pi
+
+
+def test_twin_relabelling_rule():
+    A = sp.csr_matrix(np.array([[0, 1, 1, 1, 0], [1, 0, 0, 0, 1], [1, 0, 0, 0, 1], [1, 0, 0, 0, 0], [0, 1, 1, 0, 0]], float))
+    # nodes 2 and 3 are twins (both adjacent to 1 and 5), node 4 is a leaf of 1 only
+    assert _twin_relabelling(A, np.array([[3, 1], [2, 5]]), np.array([[2, 1], [3, 5]])) == {3: 2, 1: 1, 2: 3, 5: 5}
+    assert _twin_relabelling(A, np.array([[4, 1]]), np.array([[2, 1]])) is None          # not twins
+    assert _twin_relabelling(A, np.array([[3, 1], [3, 5]]), np.array([[2, 1], [3, 5]])) is None   # inconsistent
+
+
 @pytest.mark.gpu
 def test_device_reproduces_the_reference_c1_greedy_runs():
-    """The device against the same file.  Two candidates that are structurally equivalent (two leaves of one hub) have
-    scores that coincide to the last bits, and the strict `<` of krylov_miobi.m:113 is then decided by rounding: a round
-    may legitimately pick the twin.  Required: the accumulated variation agrees to 1e-10, every round of the 'make' and
-    A7 runs picks the reference's edge, and where the k = 50 run differs the two edges share an end point (twins) -
-    at most the three rounds the diagnostics of round 1 showed (profiles/r01_diag_greedy_oregonA0_break_k50_Q250.txt)."""
+    """The device against the same file.  Two candidates that are structurally equivalent (two leaves of the same hubs)
+    have scores that coincide to the last bits, and the strict `<` of krylov_miobi.m:113 is then decided by rounding: a
+    round may legitimately pick the twin, after which the two runs continue on graphs that differ by that swap.
+    Required: the accumulated variation agrees to 1e-10 and the device's edge sequence IS the reference's up to a
+    relabelling that only permutes nodes with identical neighbourhoods (an automorphism of the graph)."""
     import krylov_robustness_b200 as kr
     ref = json.load(open(C1))
+    I = inputs()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        A7 = sp.csr_matrix(sio.loadmat(os.path.join(GOLDEN, "reference_inputs_c1.mat"))["A7"])
+    moved = {}
     for key, (e, r) in _c1_runs(kr).items():
         want = np.asarray(ref[key + "_edges"]).reshape(e.shape, order="F")
         assert abs(r - ref[key + "_rob"][0]) <= 1e-10 * abs(ref[key + "_rob"][0]), (key, r, ref[key + "_rob"][0])
-        diff = [j for j in range(e.shape[0]) if not np.array_equal(np.sort(e[j]), np.sort(want[j]))]
-        if key != "C1_A0_break_k50_Q250":
-            assert not diff, (key, diff)
-            continue
-        assert len(diff) <= 3, (key, diff, e[diff].tolist(), want[diff].tolist())
-        for j in diff:
-            assert set(e[j]) & set(want[j]), (key, j, e[j].tolist(), want[j].tolist())
+        pi = _twin_relabelling(A7 if "A7" in key else I["A0"], e, want)
+        assert pi is not None, (key, e.tolist(), want.tolist())
+        moved[key] = {a: c for a, c in pi.items() if a != c}
+    print("twin swaps:", moved)
