@@ -1,8 +1,8 @@
 """Loading the reference's data files the way its experiment scripts do (row f4 of SURVEY.md section 8).
 
 Host-side glue only (SciPy): MAT-v5 files are read with scipy.io.loadmat; the three MAT-v7.3 (HDF5) files of
-datasets_paper/Misc (CollegeMsg, Drugs, as_735) need an HDF5 reader that this image does not carry and raise a
-clear error.  Preprocessing mirrors the scripts line by line:
+datasets_paper/Misc (CollegeMsg, Drugs, as_735) go through the minimal HDF5 reader of hdf5_min.py (the image has no
+HDF5 library).  Preprocessing mirrors the scripts line by line:
 
 * unweighted experiments (Tests/test_unweighted_break.m:45-53,160-169): A <- spones(A + A'), zero diagonal,
   largest connected component (first largest label);
@@ -18,6 +18,9 @@ from scipy.sparse.csgraph import connected_components
 
 def _loadmat(path):
     import scipy.io as sio
+    from . import hdf5_min
+    if hdf5_min.is_v73(path):
+        return hdf5_min.loadmat73(path)
     try:
         return sio.loadmat(path, spmatrix=True)
     except TypeError:                      # older SciPy: no spmatrix keyword
@@ -58,7 +61,7 @@ def load_problem(path, unweighted=True):
     if var is not None:
         A = m[var]
     elif "Problem" in m:
-        A = m["Problem"]["A"][0, 0]
+        A = m["Problem"]["A"] if isinstance(m["Problem"], dict) else m["Problem"]["A"][0, 0]
     else:
         names = [k for k in m if not k.startswith("__")]
         if len(names) != 1:

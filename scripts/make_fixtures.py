@@ -47,6 +47,10 @@ def main():
         A = sp.csr_matrix(v[k]).astype(np.float64)
         A = (A + A.T) / 2 if (A != A.T).nnz else A
         save("grid_%s" % k, A / A.max())
+    # the three MAT-v7.3 (HDF5) files of datasets_paper/Misc, through the minimal HDF5 reader (hdf5_min.py)
+    from krylov_robustness_b200.datasets import load_problem
+    for k in ("Drugs", "CollegeMsg", "as_735"):
+        save("misc_%s" % k, load_problem(os.path.join(REF, "datasets_paper", "Misc", k + ".mat")))
 
 
 if __name__ == "__main__":
