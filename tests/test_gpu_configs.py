@@ -27,7 +27,10 @@ def O():
     return oracle
 
 
-@pytest.mark.parametrize("gname", ["oregon_A2", "oregon_A3", "oregon_A4", "oregon_A5", "oregon_A6", "oregon_A7"])
+# the three Misc graphs are the MAT-v7.3 files of datasets_paper/Misc (read by the minimal HDF5 reader, hdf5_min.py):
+# same trace_exp + break-round check at the call shape of Tests/test_unweighted_break.m
+@pytest.mark.parametrize("gname", ["oregon_A2", "oregon_A3", "oregon_A4", "oregon_A5", "oregon_A6", "oregon_A7",
+                                   "misc_Drugs", "misc_CollegeMsg", "misc_as_735"])
 def test_c1_oregon_trace_exp_and_break_round(kr, O, graphs, gname):
     A = graphs(gname)
     n = A.shape[0]
