@@ -6,15 +6,13 @@ restate the two MathWorks m-files the path uses (`normest`: power iteration on A
 block 1-norm estimator, written here for the t = 1 column the reference asks for) from their published algorithms."""
 import os
 import tempfile
-import warnings
 
 import numpy as np
 import scipy.io as sio
 import scipy.linalg as sla
 import scipy.sparse as sp
 
-from .values import (MatlabError, Cell, Struct, FH, EMPTY, COLON, scalar, norm_val, is_num, dense, as_float, to_float,
-                     to_int, truth)
+from .values import MatlabError, Cell, Struct, FH, EMPTY, scalar, is_num, dense, as_float, to_float, to_int
 from . import ops
 
 TABLE = {}
@@ -26,10 +24,6 @@ def builtin(*names):
             TABLE[n] = f
         return f
     return deco
-
-
-def _arg(args, k, default=None):
-    return args[k] if k < len(args) else default
 
 
 def _isstr(v, s=None):
@@ -633,11 +627,6 @@ def _sort(I, a, n):
     return out
 
 
-def _as_set_input(v):
-    v = as_float(v)
-    return v, (v.shape[0] == 1 and v.shape[1] != 1) or v.shape == (0, 0) or v.shape == (1, 1) and False
-
-
 @builtin("unique")
 def _unique(I, a, n):
     v = as_float(a[0])
@@ -969,7 +958,7 @@ def _exist(I, a, n):
         return scalar(0.0)
     if kind in (None, "file", "builtin") and (I.find_function(name, fr) is not None):
         return scalar(2.0)
-    if kind in (None, "builtin") and name in TABLE:
+    if kind in (None, "builtin") and name in I.builtins:
         return scalar(5.0)
     if kind in (None, "file", "dir") and os.path.exists(name):
         return scalar(7.0 if os.path.isdir(name) else 2.0)

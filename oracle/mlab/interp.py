@@ -6,8 +6,8 @@ import numpy as np
 import scipy.sparse as sp
 
 from .parser import parse_source, Function
-from .values import (MatlabError, COLON, Cell, Struct, FH, EMPTY, scalar, norm_val, is_num, is_scalar, dense,
-                     as_float, to_float, to_int, truth, index_get, index_set, concat)
+from .values import (MatlabError, COLON, Cell, Struct, FH, EMPTY, scalar, norm_val, is_num, dense, truth, index_get,
+                     index_set, concat)
 
 
 class _Break(Exception):
@@ -182,7 +182,7 @@ class Interpreter:
             p = caller
             while p is not None and p.fn is not fn.parent:
                 p = p.parent
-            fr.parent = p if p is not None else getattr(fn, "_home", None)
+            fr.parent = p
         for k, pname in enumerate(fn.params):
             if pname == "varargin" and k == len(fn.params) - 1:
                 fr.ws["varargin"] = Cell.row(args[k:])
@@ -218,8 +218,7 @@ class Interpreter:
             if fh.frame is not None:
                 fn = self.find_function(fh.name, fh.frame)
                 if isinstance(fn, Function):
-                    if fn.parent is not None:
-                        fn._home = fh.frame
+                    # a handle to a nested function runs in the workspace of the frame that created the handle
                     return self.call_function(fn, args, nargout, fh.frame)
             return self.call_named(fh.name, args, nargout, fh.frame)
         fr = Frame(fh.frame.fn if fh.frame is not None else None, len(args), nargout)
@@ -262,10 +261,9 @@ class Interpreter:
             elif kind == "massign":
                 lhs = st[1]
                 vals = self.eval_multi(st[2], fr, len(lhs))
-                if len(vals) < len([1 for l in lhs]) and len(vals) < len(lhs):
-                    # fewer outputs than targets is only fine when the missing ones are ~ placeholders at the end
-                    if any(l is not None for l in lhs[len(vals):]):
-                        raise MatlabError("Too many output arguments.")
+                # fewer outputs than targets is only fine when the missing ones are ~ placeholders at the end
+                if len(vals) < len(lhs) and any(l is not None for l in lhs[len(vals):]):
+                    raise MatlabError("Too many output arguments.")
                 for l, v in zip(lhs, vals):
                     if l is not None:
                         self.assign(l, v, fr)
@@ -588,7 +586,7 @@ class Interpreter:
         # name(...) where name is not a variable: a function call
         if base[0] == "id" and kind == "()" and not self.has_var(fr, base[1]) and base[1] not in ("nargin", "nargout"):
             argv = self.eval_args(args, fr)
-            return self.call_named(base[1], argv, max(nargout, 1) if nargout else (0 if nargout == 0 else 1), fr)
+            return self.call_named(base[1], argv, nargout, fr)
         obj = self.eval(base, fr)
         if kind == "()":
             if isinstance(obj, FH):

@@ -7,7 +7,7 @@ import scipy.linalg as sla
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from .values import MatlabError, norm_val, is_num, dense, as_float, scalar, Cell, FH, Struct
+from .values import MatlabError, norm_val, is_num, dense, as_float, Cell
 
 
 def _num(v, op):

@@ -2,7 +2,7 @@
 
 Produces a small tuple AST.  Operator precedence follows MATLAB's table: `||` < `&&` < `|` < `&` < comparisons < `:`
 < `+ -` < `* / \\ .* ./ .\\` < unary `+ - ~` < `^ .^` < postfix (transpose, indexing, field access)."""
-from .lexer import tokenize, Tok
+from .lexer import tokenize
 
 
 class ParseError(Exception):
