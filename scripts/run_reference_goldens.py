@@ -25,12 +25,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-SCRIPTS = {False: ("make_reference_goldens.m", "reference_golden"), True: ("make_reference_goldens_c1.m", "reference_golden_c1")}
+SCRIPTS = {"main": ("make_reference_goldens.m", "reference_golden"),
+           "c1": ("make_reference_goldens_c1.m", "reference_golden_c1"),                 # ~10 min
+           "c1trace": ("make_reference_goldens_c1_trace.m", "reference_golden_c1_trace")}  # ~5 min
 
 
-def run(refdir, out_json=None, c1=False):
+def run(refdir, out_json=None, which="main"):
     """-> (golden dict, provenance dict).  The .m script writes the JSON itself; `out_json` redirects it."""
-    script, stem = SCRIPTS[c1]
+    script, stem = SCRIPTS[which]
     from oracle.mlab import Interpreter
     interp = Interpreter(stdout=io.StringIO())
     ws = {"refdir": refdir}
@@ -58,9 +60,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--refdir", default="/root/reference")
     ap.add_argument("--check", action="store_true")
-    ap.add_argument("--c1", action="store_true", help="the long BASELINE-C1 greedy runs (make_reference_goldens_c1.m, ~10 min)")
+    ap.add_argument("--which", default="main", choices=sorted(SCRIPTS), help="main (25 s); c1: the BASELINE-C1 greedy runs; "
+                    "c1trace: trace_exp on four Oregon graphs")
+    ap.add_argument("--c1", action="store_true", help="same as --which c1")
     a = ap.parse_args()
-    stem = SCRIPTS[a.c1][1]
+    if a.c1:
+        a.which = "c1"
+    stem = SCRIPTS[a.which][1]
     if not os.path.isdir(os.path.join(a.refdir, "functions")):
         sys.exit("no reference checkout at %s" % a.refdir)
     gpath = os.path.join(ROOT, "tests", "golden", stem + ".json")
@@ -68,14 +74,14 @@ def main():
         import tempfile
         import numpy as np
         tmp = os.path.join(tempfile.mkdtemp(), "g.json")
-        fresh, _ = run(a.refdir, tmp, a.c1)
+        fresh, _ = run(a.refdir, tmp, a.which)
         stored = json.load(open(gpath))
         assert set(fresh) == set(stored), sorted(set(fresh) ^ set(stored))
         for k in fresh:
             assert np.array_equal(np.asarray(fresh[k]), np.asarray(stored[k])), k
         print("%s.json reproduced bit for bit (%d entries)" % (stem, len(fresh)))
         return
-    golden, prov = run(a.refdir, None, a.c1)
+    golden, prov = run(a.refdir, None, a.which)
     with open(os.path.join(ROOT, "tests", "golden", stem + ".provenance.json"), "w") as fh:
         json.dump(prov, fh, indent=1)
         fh.write("\n")

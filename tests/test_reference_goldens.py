@@ -376,3 +376,42 @@ def test_device_reproduces_the_reference_c1_greedy_runs():
         assert pi is not None, (key, e.tolist(), want.tolist())
         moved[key] = {a: c for a, c in pi.items() if a != c}
     print("twin swaps:", moved)
+
+
+C1T = os.path.join(GOLDEN, "reference_golden_c1_trace.json")
+
+
+def _c1_trace(P, A_of):
+    """trace_exp on Oregon A0, A4, A7, A8 with the Park-Miller sign probes of make_reference_goldens_c1_trace.m."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mri1", os.path.join(ROOT, "scripts", "make_reference_inputs_c1.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from conftest import load_graph
+    ref = json.load(open(C1T))
+    bad = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name in ("A0", "A4", "A7", "A8"):
+            A = load_graph("oregon_" + name)
+            Pm = mod.lcg_sign_probes(A.shape[0])
+            pairs = [(Pm[:, 20 * k:20 * k + 10], Pm[:, 20 * k + 10:20 * k + 20]) for k in range(34)]
+            tr = P.trace_exp(A_of(A), pairs)
+            want, used = ref["C1_trace_exp_" + name]
+            assert used % 20 == 0 and 20 <= used <= 680
+            if not abs(tr - want) <= RTOL * abs(want):
+                bad.append((name, tr, want))
+    assert not bad, bad
+
+
+def test_oracle_reproduces_the_reference_c1_trace_exp():
+    """trace_exp.m -> mc_trace.m -> expmv.m -> select_taylor_degree.m -> normAm.m run from source on four Oregon graphs
+    (the nested deflation of mc_trace.m:46-49 stacks up to 34 anonymous functions): same estimate to 1e-10."""
+    import oracle as O
+    _c1_trace(O, lambda A: A)
+
+
+@pytest.mark.gpu
+def test_device_reproduces_the_reference_c1_trace_exp():
+    import krylov_robustness_b200 as kr
+    _c1_trace(kr, lambda A: kr.Matrix(A))
