@@ -174,6 +174,54 @@ def test_control_flow_sparse_and_builtins(tmp_path):
     assert ws["st"] == "3,2.50,ok"
 
 
+def test_idioms_of_the_reference_sources(tmp_path):
+    """The exact statements the reference leans on, each with the value MATLAB's semantics prescribe."""
+    # comments name the reference lines each idiom comes from: for-range evaluated once (function_multiple_entries.m:
+    # 110,146), row deletion by index list (krylov_miobi.m:126), implicit expansion (greedy_krylov.m:66), lag buffer
+    # (trace_fun_update.m:117), `C (C == 0) = inf` and blank-separated outputs (expmv.m:63-66), sparse hash table
+    # (fun_and_grad_krylov_exp.m:52-53), stable descending sort + first match (find_top_edges.m:25-31), row() lookup
+    # (function_multiple_entries.m:45), edge2low_rank.m:6-12, `if` on a size vector (function_multiple_entries.m:122),
+    # matrix-to-handle rebinding (mc_trace.m:32-34)
+    ws, _ = run("""
+        notconv = [1 2 3 4];  seen = [];
+        for h = notconv
+            notconv = setdiff(notconv, h);
+            seen = [seen h];
+        end
+        E = [1 2; 3 4; 5 6; 7 8];  k = 2;
+        E2 = E([1:k-1, k+1:end], :);
+        tmp = [5 6];  ind = find(prod(E == tmp, 2));
+        Xstop = [1 2];  Xm = 3;  d = 2;  Xstop = [Xstop(2:d), Xm];
+        C = [0 3; 2 0; 5 1];  C (C == 0) = inf;  [cost, m] = min(min(C));
+        [cst m2] = min([4; 2; 2]);
+        aux = [3; 7; 9];  iaux = sparse(max(aux), 1);  iaux(aux) = [1:3]';  i7 = full(iaux(7));
+        c = [0.5 0.9 0.5 0.9 0.1];  [~, order] = sort(c, 'descend');
+        sc = sort(c, 'descend');  first = find(sc == c(3), 1);
+        I = unique([4; 2; 4; 9; 2], 'stable')';  row = @(t) sum((I == t) .* [1:length(I)]);  r9 = row(9);
+        t1 = [2; 2; 5];  t2 = [5; 7; 7];  ut = unique([t1; t2]);
+        U = sparse(ut, 1:length(ut), 1, 8, length(ut));  B = zeros(length(ut));
+        for j = 1:length(t1)
+            a = find(t1(j) == ut);  b = find(t2(j) == ut);  B(a, b) = -1;  B(b, a) = -1;
+        end
+        S = full(U * B * U');
+        H = reshape(1:16, 4, 4);  H(1:end-2, end-1:end) = H(1:end-2, end-1:end) + [1 1; 1 1];
+        nn = 3;  X = [1 2; 3 4];  if nn > size(X), X(nn, nn) = 0; end
+        Afun = [2 0; 0 3];  if isfloat(Afun), Afun = @(x) Afun * x; end
+        v = Afun([1; 1]);
+        n17 = sprintf('%.17g', 0.1);
+    """, tmp_path)
+    assert val(ws["seen"]) == [[1, 2, 3, 4]] and ws["notconv"].size == 0
+    assert val(ws["E2"]) == [[1, 2], [5, 6], [7, 8]] and val(ws["ind"]) == [[3]] and val(ws["Xstop"]) == [[2, 3]]
+    assert val(ws["cost"]) == [[1]] and val(ws["m"]) == [[2]] and val(ws["cst"]) == [[2]] and val(ws["m2"]) == [[2]]
+    assert val(ws["i7"]) == [[2]] and val(ws["order"]) == [[2, 4, 1, 3, 5]] and val(ws["first"]) == [[3]] and val(ws["r9"]) == [[3]]
+    S = np.zeros((8, 8))
+    for a, b in ((2, 5), (2, 7), (5, 7)):
+        S[a - 1, b - 1] = S[b - 1, a - 1] = -1
+    assert np.array_equal(ws["S"], S)
+    assert val(ws["H"])[0][2:] == [10, 14] and val(ws["H"])[1][2:] == [11, 15] and val(ws["H"])[2][2:] == [11, 15]
+    assert ws["X"].shape == (3, 3) and val(ws["v"]) == [[2], [3]] and ws["n17"] == "0.10000000000000001"
+
+
 def test_errors_carry_file_and_line(tmp_path):
     with pytest.raises(MatlabError) as e:
         run("a = [1 2 3];\nb = a(4);\n", tmp_path)
