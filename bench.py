@@ -474,13 +474,17 @@ def run_ours(args):
         peak = peak_gbs()
         src = PEAK_SOURCE[0]
         # algorithmic bytes with the matrix as it is actually stored (pattern-only CSR: 4 B per nonzero)
-        b_spmm = (4.0 if pattern_only else 12.0) * nnz + 4.0 * (n + 1) + 16.0 * n * k
+        # columns one SpMM launch covers: k unsplit; k/2 when the SLQ step runs its two column groups half a step
+        # apart (csrc/slq.cuh, split mode) - derived from the launches counted in the timed region
+        cols_per_launch = float(k) * m * args.steps / max(spmm_launches, 1)
+        b_spmm = (4.0 if pattern_only else 12.0) * nnz + 4.0 * (n + 1) + 16.0 * n * cols_per_launch
         per_launch_ms = spmm_ms / max(spmm_launches, 1)
         achieved = b_spmm / (per_launch_ms * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "spmm_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                # measured on one k = 512 launch; a launch over fewer columns moves proportionally less
+                traffic = json.load(f).get("dram_bytes_per_launch") * cols_per_launch / 512.0
         except Exception:
             pass
         # bounded CPU sample: the oracle on one core, 4 probes x m steps of the same graph
@@ -501,7 +505,8 @@ def run_ours(args):
                                 "h2d_bytes_per_step": (g1["h2d_bytes"] - g0["h2d_bytes"]) // e2e_steps,
                                 "ms_per_step": ms_e2e8 / e2e_steps, "trace_estimate": tr_e2e8},
             "gpu_launches": c1["launches"] - c0["launches"],
-            "roofline": {"bound": "hbm", "kernel": "spmm_kernel<EpiDot> (CSR x 512-wide fp64 block + fused alpha dot)",
+            "roofline": {"bound": "hbm", "kernel": "spmm_kernel<EpiDot> (CSR x %d-wide fp64 block + fused alpha dot)" % int(round(cols_per_launch)),
+                         "columns_per_launch": cols_per_launch,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "%s copy bandwidth (MEASURED_PEAKS.json)" % src if src == "measured"
                          else "fallback 6650 GB/s (B200_PROFILING.md)",
@@ -511,8 +516,8 @@ def run_ours(args):
                          # what actually binds on a random power-law graph: every
                          # (nonzero, column) operand crosses L2 -> SM once; the pure-gather ceiling on a
                          # 128 MB window was measured with scripts/l2_gather.cu
-                         "gather": {"bytes_per_launch": 8.0 * nnz * k,
-                                    "achieved_tb_per_s": 8.0 * nnz * k / (per_launch_ms * 1e-3) / 1e12,
+                         "gather": {"bytes_per_launch": 8.0 * nnz * cols_per_launch,
+                                    "achieved_tb_per_s": 8.0 * nnz * cols_per_launch / (per_launch_ms * 1e-3) / 1e12,
                                     "microbench_ceiling_tb_per_s": 14.8,
                                     "source": "profiles/r01_l2_gather_microbench.json"}},
             "secondary": secondary, "secondary_c4": secondary_c4, "strong_scaling": strong,
