@@ -182,6 +182,18 @@ out.Mexico_fg30_sinh = [fv; gr]; out.Mexico_dfA30_cosh = dfA30;
 eA30 = function_multiple_entries(in.Mexico, in.Mexico_Omega30, @exp, tolE, 100, inf, 0);
 [fv, gr] = fun_and_grad_krylov_exp(in.Mexico_X30, in.Mexico, in.Mexico_Omega30, eA30, 1e-8, 100, 0);
 out.Mexico_fg30_exp = [fv; gr]; out.Mexico_eA30 = eA30;
+% BASELINE config C2 at the reference's literal call: Omega = ALL edges of the Anaheim road network.  U becomes an
+% n x n selector, fun_update.m:84-90 takes its dense branch and trace_fun_update stops on a lucky breakdown after one
+% block step.  (The device evaluates the same gradient sparsely, fun_and_grad_all_edges; the dense cosh(A) entries that
+% the callback wants as dfA are formed here the way Tests/test_weighted_sinh_lbfgs.m does, from the dense function.)
+if ~dropin
+    fA = full(in.Anaheim);
+    Cd = (expm(fA) + expm(-fA)) / 2;
+    nA = size(fA, 1);
+    dfAn = Cd((in.Anaheim_Omega(:, 2) - 1) * nA + in.Anaheim_Omega(:, 1));
+    [fv, gr] = fun_and_grad_krylov_fun(in.Anaheim_X, in.Anaheim, in.Anaheim_Omega, @sinh, @cosh, dfAn, 1e-8, 100, 0);
+    out.Anaheim_all_edges_fg_sinh = [fv; gr];
+end
 if ~dropin
     [Umf, Xmf, Vmf, rowf, colf, itf] = multiple_frechet_eval(in.Mexico, in.Mexico_Omega, @exp, 1e-10, 100, inf, 0);
     out.Mexico_frechet_iter = itf;

@@ -66,6 +66,15 @@ def build_inputs():
     pick30 = np.sort(rng.choice(T.nnz, 30, replace=False))
     out["Mexico_Omega30"] = np.stack([T.row[pick30] + 1, T.col[pick30] + 1], 1).astype(np.float64)
     out["Mexico_X30"] = (0.1 * rng.uniform(0.0, 1.0, 30)).reshape(-1, 1)
+    # ---- fourth batch: BASELINE config C2 on the smallest Transport graph - Omega = ALL lower-triangular edges,
+    # X = 0.1 * A_Omega * uniform(0, 1) with seed 4, f = sinh, df = cosh
+    An = load_graph("transport_Anaheim")
+    An = (An / An.max()).tocsr()
+    Tn = sp.tril(An, -1).tocoo()
+    order = np.lexsort((Tn.row, Tn.col))
+    out["Anaheim"] = sp.csc_matrix(An)
+    out["Anaheim_Omega"] = np.stack([Tn.row[order] + 1, Tn.col[order] + 1], 1).astype(np.float64)
+    out["Anaheim_X"] = (0.1 * Tn.data[order] * np.random.default_rng(4).uniform(0.0, 1.0, Tn.nnz)).reshape(-1, 1)
     return out
 
 

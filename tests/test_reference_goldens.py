@@ -273,6 +273,20 @@ def _check(P, ref, A_of, device):
         # makes the reference's LAPACK calls in the reference's order and lands on the same value; the device, with
         # its own (Cholesky-QR) arithmetic, is held to the accuracy the reference's own value has there.
         C.close("Mexico_fg30_sinh objective", [fv], "Mexico_fg30_sinh", sl=slice(0, 1), rtol=1e-3 if device else RTOL)
+        # BASELINE config C2 at the reference's literal call: Omega = ALL 634 edges of the Anaheim road network (U is an
+        # n x n selector: dense branch of fun_update.m:84-90, lucky breakdown in trace_fun_update after one block step)
+        import scipy.linalg as sla
+        An, OmA, XA = I["Anaheim"], I["Anaheim_Omega"].astype(np.int64), I["Anaheim_X"].ravel()
+        dfAn = sla.coshm(An.toarray())[OmA[:, 0] - 1, OmA[:, 1] - 1]
+        fv, gr = P.fun_and_grad_krylov_fun(XA, A_of(An), OmA, "sinh", "cosh", dfAn, 1e-8, 100, 0)
+        C.close("Anaheim_all_edges objective", [fv], "Anaheim_all_edges_fg_sinh", sl=slice(0, 1))
+        C.close("Anaheim_all_edges gradient", np.ravel(gr), "Anaheim_all_edges_fg_sinh", sl=slice(1, None))
+        if hasattr(P, "fun_and_grad_all_edges"):
+            # the device's sparse formulation of the same gradient (one single-vector Krylov space per distinct row,
+            # stopped at 1e-10 * cosh(||A||)) against the reference's dense evaluation
+            gr2 = P.fun_and_grad_all_edges(XA, An, OmA, "sinh", "cosh", 1e-10 * np.cosh(float(P.normest(A_of(An), 1e-6)[0])), 100)
+            C.close("Anaheim_all_edges gradient, sparse formulation", np.ravel(gr2), "Anaheim_all_edges_fg_sinh",
+                    sl=slice(1, None), rtol=1e-9)
         C.close("Mexico_hessian_exp", P.hessianfcn_exp(Xw, I["Mexico"], Om, 1e-10, 100))
         C.close("Mexico_hessian_sinh", P.hessianfcn_fun(Xw, I["Mexico"], Om, "sinh", 1e-10, 100))
         if hasattr(P, "multiple_frechet_eval"):
