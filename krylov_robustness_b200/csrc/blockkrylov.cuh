@@ -473,7 +473,12 @@ inline TfuResult trace_fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64
     if (!is_symmetric(B)) fail(KR_ERR_UNSUPPORTED, "trace_fun_update: the device path needs a symmetric (Hermitian) B");
     ExpmWork ew;
     DevBuf<double> xm(ctx, 1);
-    if (n <= 130) {                                           // :37-51 dense branch
+    // A block as wide as the space (rk >= n: U = selector of every node, the literal "all edges" call of config C2):
+    // V = qr(U) spans everything, W = AV - V(V'AV) is zero, the reference stops at j = 1 on a lucky breakdown with
+    // Gm = V'AV, i.e. with the dense quantity below (trace_fun_update.m:62-87,119-124).
+    const bool whole_space = rk >= n && n > 130;
+    if (n <= 130 || whole_space) {                            // :37-51 dense branch
+        if (whole_space) { out.iter = 1; out.lucky = 1; }
         const HostMat fA = dense_of(M);
         const HostMat S = dense_updated(fA, rk, U, ldu, B, true);
         std::vector<double> both((size_t)2 * n * n);
@@ -548,6 +553,29 @@ inline FuInfo fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64_t rk, co
     FuInfo info;
     if (!is_symmetric(B)) fail(KR_ERR_UNSUPPORTED, "fun_update: the device path needs a symmetric (Hermitian) B");
     ExpmWork ew;
+    auto dense_fallback = [&](int64_t j, int lucky) {          // :85-90: f(A + U B U') - f(A) in dense arithmetic, Um = I
+        const HostMat fA = dense_of(M);
+        const HostMat fAt = dense_updated(fA, rk, U, ldu, B, false);
+        std::vector<double> both((size_t)2 * n * n);
+        std::copy(fAt.a.begin(), fAt.a.end(), both.begin());
+        std::copy(fA.a.begin(), fA.a.end(), both.begin() + (size_t)n * n);
+        DevBuf<double> dS(ctx, both.size()), dF(ctx, both.size());
+        dS.upload(both.data(), both.size());
+        symfun_batched(ctx, dS.p, (int)n, 2, fun, std::max(host_norm1(fAt), host_norm1(fA)), dF.p, ew);
+        res.Xm.reset(ctx, (size_t)n * n);
+        KR_LAUNCH(ctx, axpby_kernel, ew_grid(ctx, n * n), 256, 0, res.Xm.p, 1.0, dF.p, -1.0, dF.p + (size_t)n * n, n * n);
+        KR_CUDA(cudaStreamSynchronize(ctx->stream));
+        res.n = n; res.dim = n; res.bs = rk; res.identity_basis = true; res.has_basis = true;
+        info.dim = n; info.iter = j; info.lucky = lucky; info.dense_fallback = 1;
+    };
+    // A block wider than the QR kernels take (HQR_MAXB) whose first Arnoldi step already saturates the space
+    // (2 * 2rk >= n): the reference leaves through its dense branch at j = 1 whatever the step produced, so the step
+    // is not needed.  lucky is what the step would report for a connected graph: W vanishes only when the block
+    // spans everything.
+    if (want_basis && rk > HQR_MAXB && 4 * rk >= n) {
+        dense_fallback(1, rk >= n ? 1 : 0);
+        return info;
+    }
     WideSetup ws = wide_setup(ctx, M, rk, U, ldu, B, want_basis);
     kr_krylov* st = ws.st.get();
     std::vector<DevBuf<double>> Xs;                            // Xm of every step (the lag-2 test needs j-2)
@@ -561,19 +589,7 @@ inline FuInfo fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64_t rk, co
         if (wide_prof().on) { KR_CUDA(cudaStreamSynchronize(ctx->stream)); wide_prof().step += WideProf::now() - t0; wide_prof().n_step++; }
         if (want_basis && 2 * st->vcols() >= n) {               // :85-90 dense fallback
             sync_lucky(st);
-            const HostMat fA = dense_of(M);
-            const HostMat fAt = dense_updated(fA, rk, U, ldu, B, false);
-            std::vector<double> both((size_t)2 * n * n);
-            std::copy(fAt.a.begin(), fAt.a.end(), both.begin());
-            std::copy(fA.a.begin(), fA.a.end(), both.begin() + (size_t)n * n);
-            DevBuf<double> dS(ctx, both.size()), dF(ctx, both.size());
-            dS.upload(both.data(), both.size());
-            symfun_batched(ctx, dS.p, (int)n, 2, fun, std::max(host_norm1(fAt), host_norm1(fA)), dF.p, ew);
-            res.Xm.reset(ctx, (size_t)n * n);
-            KR_LAUNCH(ctx, axpby_kernel, ew_grid(ctx, n * n), 256, 0, res.Xm.p, 1.0, dF.p, -1.0, dF.p + (size_t)n * n, n * n);
-            KR_CUDA(cudaStreamSynchronize(ctx->stream));
-            res.n = n; res.dim = n; res.bs = rk; res.identity_basis = true; res.has_basis = true;
-            info.dim = n; info.iter = j; info.lucky = st->lucky; info.dense_fallback = 1;
+            dense_fallback(j, st->lucky);
             return info;
         }
         const int nn = (int)(j * rk);

@@ -186,14 +186,12 @@ out.Mexico_fg30_exp = [fv; gr]; out.Mexico_eA30 = eA30;
 % n x n selector, fun_update.m:84-90 takes its dense branch and trace_fun_update stops on a lucky breakdown after one
 % block step.  (The device evaluates the same gradient sparsely, fun_and_grad_all_edges; the dense cosh(A) entries that
 % the callback wants as dfA are formed here the way Tests/test_weighted_sinh_lbfgs.m does, from the dense function.)
-if ~dropin
-    fA = full(in.Anaheim);
-    Cd = (expm(fA) + expm(-fA)) / 2;
-    nA = size(fA, 1);
-    dfAn = Cd((in.Anaheim_Omega(:, 2) - 1) * nA + in.Anaheim_Omega(:, 1));
-    [fv, gr] = fun_and_grad_krylov_fun(in.Anaheim_X, in.Anaheim, in.Anaheim_Omega, @sinh, @cosh, dfAn, 1e-8, 100, 0);
-    out.Anaheim_all_edges_fg_sinh = [fv; gr];
-end
+fA = full(in.Anaheim);
+Cd = (expm(fA) + expm(-fA)) / 2;
+nA = size(fA, 1);
+dfAn = Cd((in.Anaheim_Omega(:, 2) - 1) * nA + in.Anaheim_Omega(:, 1));
+[fv, gr] = fun_and_grad_krylov_fun(in.Anaheim_X, in.Anaheim, in.Anaheim_Omega, @sinh, @cosh, dfAn, 1e-8, 100, 0);
+out.Anaheim_all_edges_fg_sinh = [fv; gr];
 if ~dropin
     [Umf, Xmf, Vmf, rowf, colf, itf] = multiple_frechet_eval(in.Mexico, in.Mexico_Omega, @exp, 1e-10, 100, inf, 0);
     out.Mexico_frechet_iter = itf;
