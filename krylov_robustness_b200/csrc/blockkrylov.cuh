@@ -95,7 +95,7 @@ __global__ void add_inplace_kernel(double* __restrict__ a, const double* __restr
 __global__ void __launch_bounds__(256)
 hsub_lucky_kernel(const double* __restrict__ R, int bs, int bpad, double* __restrict__ Rp, int arnoldi, int* __restrict__ lucky) {
     __shared__ double red[256];
-    __shared__ double x[HQR_MAXB], y[HQR_MAXB];
+    __shared__ double x[HQR_WIDEB], y[HQR_WIDEB];
     double s = 0.0;
     for (int e = threadIdx.x; e < bpad * bpad; e += 256) {
         const int i = e % bpad, j = e / bpad;
@@ -117,7 +117,7 @@ hsub_lucky_kernel(const double* __restrict__ R, int bs, int bpad, double* __rest
     else if (fro / sqrt((double)bs) >= 1e-12) lk = 0;
     else if (fro < 1e-12) lk = 1;
     else {
-        // ||R||_2 by power iteration on R'R (bs <= 128; a rare path, right at a breakdown)
+        // ||R||_2 by power iteration on R'R (bs <= HQR_WIDEB; a rare path, right at a breakdown)
         for (int i = threadIdx.x; i < bs; i += 256) x[i] = 1.0;
         __syncthreads();
         double lam = 0.0;
@@ -360,7 +360,7 @@ inline std::unique_ptr<kr_krylov> krylov_start(kr_ctx* ctx, const kr_matrix* A, 
     const int64_t n = A->dev.n;
     if (b->n != n) fail(KR_ERR_ARG, "The block vector b has wrong number of rows");
     if (bs < 1) fail(KR_ERR_ARG, "empty starting block");
-    if (bs > HQR_MAXB) fail(KR_ERR_UNSUPPORTED, "block width %lld exceeds %d", (long long)bs, HQR_MAXB);
+    if (bs > HQR_WIDEB) fail(KR_ERR_UNSUPPORTED, "block width %lld exceeds %d", (long long)bs, HQR_WIDEB);
     std::unique_ptr<kr_krylov> st(new kr_krylov());
     st->ctx = ctx; st->A = A; st->arnoldi = arnoldi; st->n = n; st->bs = bs;
     st->bp = b->panels;
@@ -568,11 +568,11 @@ inline FuInfo fun_update_general(kr_ctx* ctx, const kr_matrix* M, int64_t rk, co
         res.n = n; res.dim = n; res.bs = rk; res.identity_basis = true; res.has_basis = true;
         info.dim = n; info.iter = j; info.lucky = lucky; info.dense_fallback = 1;
     };
-    // A block wider than the QR kernels take (HQR_MAXB) whose first Arnoldi step already saturates the space
+    // A block wider than the QR kernels take (HQR_WIDEB) whose first Arnoldi step already saturates the space
     // (2 * 2rk >= n): the reference leaves through its dense branch at j = 1 whatever the step produced, so the step
     // is not needed.  lucky is what the step would report for a connected graph: W vanishes only when the block
     // spans everything.
-    if (want_basis && rk > HQR_MAXB && 4 * rk >= n) {
+    if (want_basis && rk > HQR_WIDEB && 4 * rk >= n) {
         dense_fallback(1, rk >= n ? 1 : 0);
         return info;
     }

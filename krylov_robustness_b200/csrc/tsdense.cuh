@@ -252,7 +252,10 @@ inline void ts_rightmul(kr_ctx* ctx, const PanelList& V, const PanelList& W, int
 //   - accumulate, over the rows below the NEW diagonal row k, dots[j] = sum_r W(r,k) W(r,j), j = k .. bs-1.
 // Pass k of the form-Q phase (dorg2r, k = bs-1 .. 0, plus one leading dots-only pass) works the same way with
 // the reflectors read back from the strictly lower part of W.
-constexpr int HQR_MAXB = 128;        // widest block
+constexpr int HQR_MAXB = 128;        // widest block of the default instantiation
+constexpr int HQR_WIDEB = 256;       // widest block at all: the second instantiation, for the edge sets of the budget
+                                     // scripts (Tests/test_unweighted_break_budget.m:89-90,119-120: up to 100 edges,
+                                     // i.e. up to 200 selector columns); half the threads keep its shared memory static
 constexpr int HQR_THREADS = 1024;    // 32 warps, one row per warp at a time: the passes are latency-bound (a row's
 constexpr int HQR_ROWS = 128;        // reflector entry is a dependent load), so few rows per warp = 4; larger n: see HqrWork::prepare
 
@@ -260,8 +263,8 @@ struct HqrState {
     double* R;          // [bs*bs]
     double* tau;        // [bs]
     double* beta;       // [bs] diagonal of R
-    double* partial;    // [2][nctas][HQR_MAXB] ping-pong
-    double* pivot;      // [2][HQR_MAXB] row k of the trailing matrix (written by the CTA that owns row k)
+    double* partial;    // [2][nctas][MAXB] ping-pong (MAXB = HQR_MAXB or HQR_WIDEB, the kernels' template argument)
+    double* pivot;      // [2][MAXB] row k of the trailing matrix (written by the CTA that owns row k)
 };
 
 // element (r, c) of a block given as a panel list
@@ -271,24 +274,25 @@ __device__ __forceinline__ double* hqr_at(const PanelList& W, int64_t r, int c) 
 
 // Factor pass k (0 <= k <= bs).  Reflector k-1 is defined by: alpha = pivot value W(k-1,k-1) (pass k-1 saved the
 // pivot row), xnorm^2 = dots[k-1], and for j >= k: d_j = dots[j] (over rows below k-1), W(k-1, j) = pivot[j].
-__global__ void __launch_bounds__(HQR_THREADS)
+template <int MAXB, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nctas, int rows_per_cta) {
-    __shared__ double coef[HQR_MAXB];      // tau * s_j for the trailing columns of reflector k-1
-    __shared__ double sdots[HQR_MAXB];
-    __shared__ double wred[HQR_THREADS / 32][HQR_MAXB];
+    __shared__ double coef[MAXB];      // tau * s_j for the trailing columns of reflector k-1
+    __shared__ double sdots[MAXB];
+    __shared__ double wred[THREADS / 32][MAXB];
     __shared__ double s_scale, s_tau;
     const int tid = threadIdx.x;
     const int pp = k & 1;                                  // this pass writes partial/pivot set pp, reads pp^1
-    const double* pin = st.partial + (size_t)(pp ^ 1) * nctas * HQR_MAXB;
-    double* pout = st.partial + (size_t)pp * nctas * HQR_MAXB;
-    const double* pivin = st.pivot + (pp ^ 1) * HQR_MAXB;
-    double* pivout = st.pivot + pp * HQR_MAXB;
+    const double* pin = st.partial + (size_t)(pp ^ 1) * nctas * MAXB;
+    double* pout = st.partial + (size_t)pp * nctas * MAXB;
+    const double* pivin = st.pivot + (pp ^ 1) * MAXB;
+    double* pivout = st.pivot + pp * MAXB;
     if (k > 0) {
         // dots of pass k-1, summed in CTA order
-        for (int j = tid; j < bs; j += HQR_THREADS) {
+        for (int j = tid; j < bs; j += THREADS) {
             double s = 0.0;
             if (j >= k - 1)
-                for (int c = 0; c < nctas; ++c) s += pin[(size_t)c * HQR_MAXB + j];
+                for (int c = 0; c < nctas; ++c) s += pin[(size_t)c * MAXB + j];
             sdots[j] = s;
         }
         __syncthreads();
@@ -312,7 +316,7 @@ hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int n
         }
         __syncthreads();
         const double tau = s_tau, scale = s_scale;
-        for (int j = tid; j < bs; j += HQR_THREADS) {
+        for (int j = tid; j < bs; j += THREADS) {
             double cf = 0.0;
             if (j >= k) {
                 const double sj = pivin[j] + scale * sdots[j];     // v' W(:, j), v(1) = 1
@@ -326,11 +330,11 @@ hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int n
     // rows of this CTA
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + (int64_t)rows_per_cta);
     const int warp = tid >> 5, lane = tid & 31;
-    double acc[HQR_MAXB / 32];
+    double acc[MAXB / 32];
 #pragma unroll
-    for (int t = 0; t < HQR_MAXB / 32; ++t) acc[t] = 0.0;
+    for (int t = 0; t < MAXB / 32; ++t) acc[t] = 0.0;
     const double scale = k > 0 ? s_scale : 0.0;
-    for (int64_t r = r0 + warp; r < r1; r += HQR_THREADS / 32) {
+    for (int64_t r = r0 + warp; r < r1; r += THREADS / 32) {
         double v = 0.0;
         if (k > 0 && r > k - 1) {
             double* pv = hqr_at(W, r, k - 1);
@@ -345,7 +349,7 @@ hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int n
             if (k > 0 && r > k - 1) xk -= coef[k] * v;
         }
 #pragma unroll
-        for (int t = 0; t < HQR_MAXB / 32; ++t) {
+        for (int t = 0; t < MAXB / 32; ++t) {
             const int j = lane + 32 * t;
             if (j >= k && j < bs) {
                 double* pw = hqr_at(W, r, j);
@@ -362,12 +366,12 @@ hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int n
     if (k >= bs) return;
     // CTA partial dots in warp order
 #pragma unroll
-    for (int t = 0; t < HQR_MAXB / 32; ++t) wred[warp][lane + 32 * t] = acc[t];
+    for (int t = 0; t < MAXB / 32; ++t) wred[warp][lane + 32 * t] = acc[t];
     __syncthreads();
-    for (int j = tid; j < HQR_MAXB; j += HQR_THREADS) {
+    for (int j = tid; j < MAXB; j += THREADS) {
         double s = 0.0;
-        for (int w = 0; w < HQR_THREADS / 32; ++w) s += wred[w][j];
-        pout[(size_t)blockIdx.x * HQR_MAXB + j] = s;
+        for (int w = 0; w < THREADS / 32; ++w) s += wred[w][j];
+        pout[(size_t)blockIdx.x * MAXB + j] = s;
     }
 }
 
@@ -376,19 +380,20 @@ hqr_factor_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int n
 // previous pass (pass k+1, or the leading dots-only pass when k = bs-1 has none to apply to).
 //   Q(k:, j) -= tau_k v_k dots[j]  (j > k);  Q(k,k) = 1 - tau_k;  Q(k+1:, k) = -tau_k v_k;  Q(0:k-1, k) = 0
 // and the pass accumulates dots'[j] = v_{k-1}' Q(k-1:, j) for j >= k for the next one.
-__global__ void __launch_bounds__(HQR_THREADS)
+template <int MAXB, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 hqr_formq_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nctas, int rows_per_cta) {
-    __shared__ double coef[HQR_MAXB];
-    __shared__ double wred[HQR_THREADS / 32][HQR_MAXB];
+    __shared__ double coef[MAXB];
+    __shared__ double wred[THREADS / 32][MAXB];
     const int tid = threadIdx.x;
     const int pp = k & 1;
-    const double* pin = st.partial + (size_t)(pp ^ 1) * nctas * HQR_MAXB;
-    double* pout = st.partial + (size_t)pp * nctas * HQR_MAXB;
+    const double* pin = st.partial + (size_t)(pp ^ 1) * nctas * MAXB;
+    double* pout = st.partial + (size_t)pp * nctas * MAXB;
     const double tau = st.tau[k];
-    for (int j = tid; j < bs; j += HQR_THREADS) {
+    for (int j = tid; j < bs; j += THREADS) {
         double s = 0.0;
         if (j > k)
-            for (int c = 0; c < nctas; ++c) s += pin[(size_t)c * HQR_MAXB + j];
+            for (int c = 0; c < nctas; ++c) s += pin[(size_t)c * MAXB + j];
         coef[j] = tau * s;
     }
     __syncthreads();
@@ -396,10 +401,10 @@ hqr_formq_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nc
     (void)tau_prev;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(n, r0 + (int64_t)rows_per_cta);
     const int warp = tid >> 5, lane = tid & 31;
-    double acc[HQR_MAXB / 32];
+    double acc[MAXB / 32];
 #pragma unroll
-    for (int t = 0; t < HQR_MAXB / 32; ++t) acc[t] = 0.0;
-    for (int64_t r = r0 + warp; r < r1; r += HQR_THREADS / 32) {
+    for (int t = 0; t < MAXB / 32; ++t) acc[t] = 0.0;
+    for (int64_t r = r0 + warp; r < r1; r += THREADS / 32) {
         // v_k(r): 0 above row k, 1 at row k, stored value below
         const double vk = r < k ? 0.0 : (r == k ? 1.0 : *hqr_at(W, r, k));
         // v_{k-1}(r) for the next pass' dots
@@ -407,7 +412,7 @@ hqr_formq_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nc
         if (k > 0) vp = r < k - 1 ? 0.0 : (r == k - 1 ? 1.0 : *hqr_at(W, r, k - 1));
         __syncwarp();
 #pragma unroll
-        for (int t = 0; t < HQR_MAXB / 32; ++t) {
+        for (int t = 0; t < MAXB / 32; ++t) {
             const int j = lane + 32 * t;
             if (j >= k && j < bs) {
                 double* pq = hqr_at(W, r, j);
@@ -424,12 +429,12 @@ hqr_formq_pass_kernel(PanelList W, int64_t n, int bs, int k, HqrState st, int nc
     }
     if (k == 0) return;
 #pragma unroll
-    for (int t = 0; t < HQR_MAXB / 32; ++t) wred[warp][lane + 32 * t] = acc[t];
+    for (int t = 0; t < MAXB / 32; ++t) wred[warp][lane + 32 * t] = acc[t];
     __syncthreads();
-    for (int j = tid; j < HQR_MAXB; j += HQR_THREADS) {
+    for (int j = tid; j < MAXB; j += THREADS) {
         double s = 0.0;
-        for (int w = 0; w < HQR_THREADS / 32; ++w) s += wred[w][j];
-        pout[(size_t)blockIdx.x * HQR_MAXB + j] = s;
+        for (int w = 0; w < THREADS / 32; ++w) s += wred[w][j];
+        pout[(size_t)blockIdx.x * MAXB + j] = s;
     }
 }
 
@@ -440,37 +445,44 @@ __global__ void hqr_clear_kernel(double* p, size_t count) {
 struct HqrWork {
     DevBuf<double> buf;
     HqrState st;
-    int nctas = 0, bs = 0, rows_per_cta = HQR_ROWS;
+    int nctas = 0, bs = 0, rows_per_cta = HQR_ROWS, maxb = HQR_MAXB;
     void prepare(kr_ctx* ctx, int64_t n, int bs_) {
         bs = bs_;
+        maxb = bs <= HQR_MAXB ? HQR_MAXB : HQR_WIDEB;
         // every CTA of a pass first sums the previous pass' per-CTA partial dots (nctas x bs loads): keep nctas at two
         // waves of resident CTAs instead of n / 128 (n = 200 k: 1 563 CTAs, 0.4 ms per pass, most of it that prologue)
         rows_per_cta = (int)std::max<int64_t>(HQR_ROWS, ceil_div(ceil_div(n, (int64_t)2 * ctx->num_sms), 32) * 32);
         nctas = (int)std::max<int64_t>(1, ceil_div(n, rows_per_cta));
-        const size_t need = (size_t)bs * bs + 2 * (size_t)bs + 2 * (size_t)nctas * HQR_MAXB + 2 * HQR_MAXB;
+        const size_t need = (size_t)bs * bs + 2 * (size_t)bs + 2 * (size_t)nctas * maxb + 2 * (size_t)maxb;
         if (buf.count < need) buf.reset(ctx, need);
         double* d = buf.p;
         st.R = d; d += (size_t)bs * bs;
         st.tau = d; d += bs;
         st.beta = d; d += bs;
-        st.partial = d; d += 2 * (size_t)nctas * HQR_MAXB;
+        st.partial = d; d += 2 * (size_t)nctas * maxb;
         st.pivot = d;
     }
 };
 
 // W (n x bs, panel list, padded columns zero) <- Q of the thin Householder QR; work.st.R holds R afterwards.
-inline void hqr_thin(kr_ctx* ctx, const PanelList& W, int64_t n, int bs, HqrWork& work) {
-    if (bs > HQR_MAXB) fail(KR_ERR_UNSUPPORTED, "thin QR: block width %d exceeds %d", bs, HQR_MAXB);
-    if (n < bs) fail(KR_ERR_UNSUPPORTED, "thin QR needs n >= block size");
-    work.prepare(ctx, n, bs);
+template <int MAXB, int THREADS>
+inline void hqr_thin_impl(kr_ctx* ctx, const PanelList& W, int64_t n, int bs, HqrWork& work) {
     KR_LAUNCH(ctx, hqr_clear_kernel, 8, 256, 0, work.buf.p, work.buf.count);
     for (int k = 0; k <= bs; ++k)
-        KR_LAUNCH(ctx, hqr_factor_pass_kernel, work.nctas, HQR_THREADS, 0, W, n, bs, k, work.st, work.nctas, work.rows_per_cta);
+        KR_LAUNCH(ctx, (hqr_factor_pass_kernel<MAXB, THREADS>), work.nctas, THREADS, 0, W, n, bs, k, work.st, work.nctas, work.rows_per_cta);
     // dorg2r: a leading pass that only accumulates v_{bs-1}' Q(:, j) is unnecessary (no columns to the right of
     // bs-1), but the partial set read by pass bs-1 must be zero: pass k reads set (k&1)^1
-    KR_LAUNCH(ctx, hqr_clear_kernel, 8, 256, 0, work.st.partial, 2 * (size_t)work.nctas * HQR_MAXB);
+    KR_LAUNCH(ctx, hqr_clear_kernel, 8, 256, 0, work.st.partial, 2 * (size_t)work.nctas * MAXB);
     for (int k = bs - 1; k >= 0; --k)
-        KR_LAUNCH(ctx, hqr_formq_pass_kernel, work.nctas, HQR_THREADS, 0, W, n, bs, k, work.st, work.nctas, work.rows_per_cta);
+        KR_LAUNCH(ctx, (hqr_formq_pass_kernel<MAXB, THREADS>), work.nctas, THREADS, 0, W, n, bs, k, work.st, work.nctas, work.rows_per_cta);
+}
+
+inline void hqr_thin(kr_ctx* ctx, const PanelList& W, int64_t n, int bs, HqrWork& work) {
+    if (bs > HQR_WIDEB) fail(KR_ERR_UNSUPPORTED, "thin QR: block width %d exceeds %d", bs, HQR_WIDEB);
+    if (n < bs) fail(KR_ERR_UNSUPPORTED, "thin QR needs n >= block size");
+    work.prepare(ctx, n, bs);
+    if (work.maxb == HQR_MAXB) hqr_thin_impl<HQR_MAXB, HQR_THREADS>(ctx, W, n, bs, work);
+    else hqr_thin_impl<HQR_WIDEB, HQR_THREADS / 2>(ctx, W, n, bs, work);
 }
 
 // ------------------------------------------------------------------------------------ CholQR2 + Householder signs
@@ -605,8 +617,7 @@ inline void thin_qr(kr_ctx* ctx, PanelBuf& Wb, int bs, ThinQrWork& work) {
         hqr_thin(ctx, W, n, bs, work.hqr);
         return;
     }
-    if (bs > HQR_MAXB) fail(KR_ERR_UNSUPPORTED, "thin QR: block width %d exceeds %d", bs, HQR_MAXB);
-    work.hqr.prepare(ctx, n, bs);
+    work.hqr.prepare(ctx, n, bs);                      // bs <= CQ_MAXB here
     const int ld = Wb.panels * PW;
     const size_t msz = (size_t)ld * ld;
     if (work.G.count < msz) { work.G.reset(ctx, msz); work.R1.reset(ctx, msz); work.Minv.reset(ctx, msz); }

@@ -217,6 +217,33 @@ def test_trace_fun_update_edge_set(kr, O, graphs):
     assert abs(x - ox) <= RTOL * abs(ox)
 
 
+@pytest.mark.parametrize("gname", ["transport_Rome", "oregon_A7", "misc_as_735"])
+def test_trace_fun_update_wide_edge_set(kr, O, graphs, gname):
+    """Tests/test_unweighted_break_budget.m:89-90,119-120: edge2low_rank of up to 100 edges, i.e. up to 200 selector
+    columns in ONE block (here 195 / 162 / 161; round 2 refused blocks beyond 128 columns until the Householder passes
+    got a 256-column instantiation).  With blocks this wide the reference orthogonalises against two blocks only and
+    its own value is rounding-determined: 0.07 % (Rome) to 14 % (as_735) from the dense truth, and the ORACLE's value on
+    as_735 moves by 0.2 % between two hosts (different BLAS threading).  Device and oracle are therefore held to each
+    other at 5 % with equal iteration counts (observed 1e-3 .. 1.3e-2); that the call runs at all is the point."""
+    import scipy.sparse as sp
+    A = graphs(gname)
+    n = A.shape[0]
+    T = sp.tril(A, -1).tocoo()
+    pick = np.sort(np.random.default_rng(5).choice(T.nnz, 100, replace=False))
+    E = np.stack([T.row[pick] + 1, T.col[pick] + 1], 1)
+    U, B = O.edge2low_rank(E, n)
+    assert 128 < U.shape[1] <= 200
+    nrm, _ = O.normest(A, 1e-2)
+    tol = 1e-6 * np.exp(nrm)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ox, oit, olk = O.trace_fun_update(A, U.toarray(), B, tol)
+        x, it, lk = kr.trace_fun_update(A, U.toarray(), B, tol)
+    print(gname, "rk", U.shape[1], "device", x, it, lk, "oracle", ox, oit, olk, "rel", abs(x - ox) / abs(ox))
+    assert abs(it - oit) <= 1 and bool(lk) == bool(olk)
+    assert abs(x - ox) <= 5e-2 * abs(ox)
+
+
 # ------------------------------------------------------------------ fun_update / entries / gradients
 @pytest.mark.parametrize("fun", ["exp", "cosh"])
 def test_fun_update_arnoldi_vs_oracle(kr, O, graphs, fun):
