@@ -43,15 +43,20 @@ def _eig_sorted(M):
     # MATLAB eig() of an exactly symmetric matrix takes the symmetric path; otherwise general.
     if np.array_equal(M, M.T):
         return np.linalg.eigvalsh(M)
-    return np.sort(np.linalg.eigvals(M).real)
+    # a non-Hermitian B (never on the device path, which rejects it) makes the projection unsymmetric: MATLAB's eig
+    # returns complex eigenvalues and sort() orders them by modulus, then phase; the trace formula is evaluated in
+    # complex arithmetic and its imaginary parts cancel over the conjugate pairs (found by the differential test
+    # against the reference's sources, tests/test_mlab_differential.py: taking real parts first changes the value)
+    w = np.linalg.eigvals(M)
+    return w[np.lexsort((np.angle(w), np.abs(w)))]
 
 
 def _trace_formula(name, d1, d2):
     # trace_fun_update.m:43-47 / :85-89
     if name == "exp":
-        return float(np.sum(np.exp(d1) * (1.0 - np.exp(d2 - d1))))
+        return float(np.real(np.sum(np.exp(d1) * (1.0 - np.exp(d2 - d1)))))
     f = _SCALAR[name]
-    return float(np.sum(f(d1) - f(d2)))
+    return float(np.real(np.sum(f(d1) - f(d2))))
 
 
 def _matfun(name):
