@@ -47,6 +47,52 @@ def test_trace_fun_update_random(kr, O, seed):
     close([x], [ox])
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_candidate_batches_random_both_pipelines(kr, O, seed, monkeypatch):
+    """kr_trace_fun_update_edges on random candidate lists (existing and missing edges, a self loop, a repeated
+    candidate) of weighted / unweighted graphs, through the single-launch path (one persistent CTA per candidate) AND
+    the batched slot pipeline (KR_PAIR_SLOTS), with iteration caps that some candidates hit."""
+    rng = np.random.default_rng(700 + seed)
+    n = int(rng.integers(200, 3000))
+    A = graph(rng, n, deg=float(rng.choice([3.0, 6.0, 12.0])), weighted=seed % 2 == 1, loops=4 if seed % 4 == 3 else 0)
+    m = int(rng.integers(20, 70))
+    E = np.stack([rng.integers(1, n + 1, m), rng.integers(1, n + 1, m)], 1).astype(np.int64)
+    E[3] = [E[0, 0], E[0, 0]]                                  # self loop (rank-one update, not rescaled)
+    E[5] = E[1]                                                # a repeated candidate
+    sgn = -1.0 if seed % 2 == 0 else 1.0
+    b_off = sgn / (2.0 if seed % 3 == 0 else 1.0)              # rescale = 2 every third case
+    it = int(rng.choice([4, 100]))
+    nrm = O.normest(A, 1e-2)[0]
+    tol = 10.0 ** rng.integers(-9, -5) * float(np.exp(nrm))
+    ox, oit, olk = np.zeros(m), np.zeros(m, dtype=np.int64), np.zeros(m, dtype=bool)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for h, (i, j) in enumerate(E):
+            if i != j:
+                U = np.zeros((n, 2))
+                U[i - 1, 0] = U[j - 1, 1] = 1.0
+                Bm = b_off * np.array([[0.0, 1.0], [1.0, 0.0]])
+            else:
+                U = np.zeros((n, 1))
+                U[i - 1, 0] = 1.0
+                Bm = np.array([[sgn]])
+            ox[h], oit[h], olk[h] = O.trace_fun_update(A, U, Bm, tol, it, 0, "exp")
+        M = kr.Matrix(A)
+        runs = [kr.trace_fun_update_edges(M, E, b_off, tol, it, "exp", b_self=sgn)]
+        monkeypatch.setenv("KR_PAIR_SLOTS", "16")
+        runs.append(kr.trace_fun_update_edges(M, E, b_off, tol, it, "exp", b_self=sgn))
+        monkeypatch.delenv("KR_PAIR_SLOTS")
+    deg = np.diff(A.indptr)
+    nbr = [set(A.indices[A.indptr[v]:A.indptr[v + 1]].tolist()) | {v} for v in range(n)]
+    # rank-deficient first blocks (a leaf end point; adjacent twins) are the documented LAPACK-completion cases
+    special = np.array([deg[i - 1] <= 1 or deg[j - 1] <= 1 or (i != j and nbr[i - 1] == nbr[j - 1]) for i, j in E])
+    for x, itr, lk in runs:
+        assert np.array_equal(itr, oit) and np.array_equal(np.asarray(lk, dtype=bool), olk)
+        err = np.abs(x - ox)
+        assert np.all(err[~special] <= 1e-10 * np.maximum(np.abs(ox[~special]), 1e-3 * tol)), (err / np.abs(ox)).max()
+        assert np.all(err[special] <= 1e-7 * np.maximum(np.abs(ox[special]), tol))
+
+
 @pytest.mark.parametrize("seed", range(5))
 def test_callbacks_and_hessians_random(kr, O, seed):
     rng = np.random.default_rng(200 + seed)
