@@ -71,6 +71,19 @@ out.A0_normest = normest(in.A0, 1e-2);
 for j = 2:4, [V, H, p] = lanczos_krylov(V, H, p); end
 G = H(1:end - 3, :); out.A0_lanczos_ritz = sort(eig((G + G') / 2));
 
+% ---- the operator plug-in point of the L1 functions (lanczos_krylov.m:32,78-79: A may be a struct with a `multiply`
+%      field).  Drop-in mode only: kr_operator(A) builds that struct around the device SpMM; the keys it writes are
+%      compared with A0_lanczos_ritz above and with A0 * b.
+if dropin
+    op = kr_operator(in.A0);
+    [V, H, p] = lanczos_krylov(op, in.A0_b);
+    for j = 2:4, [V, H, p] = lanczos_krylov(V, H, p); end
+    G = H(1:end - 3, :); out.A0_lanczos_ritz_operator_struct = sort(eig((G + G') / 2));
+    [V, K, H, p] = arnoldi_krylov(op, in.A0_b);
+    G = H(1:end - 3, :); out.A0_arnoldi_first_block_operator_struct = sort(eig((G + G') / 2));
+    y = op.multiply(1.0, 0.0, in.A0_b); out.A0_operator_multiply = y(:);
+end
+
 % ---- mc_trace with replayed probes
 shim = tempname(); mkdir(shim);
 fid = fopen(fullfile(shim, 'randn.m'), 'w');

@@ -127,5 +127,18 @@ def test_generator_script_through_the_wrappers_reproduces_the_reference(tmp_path
         err = np.max(np.abs(w - g)) / (scale if scale > 0 else 1.0) if w.size else 0.0
         if not err <= 1e-10:
             bad.append("%s: rel err %.3e" % (k, err))
+    # the operator plug-in point (lanczos_krylov.m:32,78-79): kr_operator(A) through the L1 wrappers gives the same
+    # projections as the matrix, and its `multiply` handle is the device SpMM
+    import scipy.io as sio
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        inp = sio.loadmat(os.path.join(GOLDEN, "reference_inputs.mat"))
+    w = np.asarray(ref["A0_lanczos_ritz"])
+    g = np.asarray(got["A0_lanczos_ritz_operator_struct"])
+    assert g.shape == w.shape and np.max(np.abs(g - w)) <= 1e-10 * np.max(np.abs(w))
+    y = (inp["A0"] @ inp["A0_b"]).ravel(order="F")
+    assert np.max(np.abs(np.asarray(got["A0_operator_multiply"]) - y)) <= 1e-13 * np.max(np.abs(y)) * 50
+    assert len(got["A0_arnoldi_first_block_operator_struct"]) == 3 and H.calls.get("spmm", 0) >= 1
     assert n >= 40, n
     assert not bad, "%d of %d keys differ from the reference's outputs:\n  %s" % (len(bad), n, "\n  ".join(bad))
