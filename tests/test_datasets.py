@@ -62,3 +62,22 @@ def test_v73_files_through_the_minimal_hdf5_reader():
             S.eliminate_zeros()
             assert (S != sp.csr_matrix(raw["W"])).nnz == 0
     assert not is_v73(os.path.join(REF, "datasets_paper", "Misc", "jazz.mat"))
+
+
+def test_hdf5_reader_rejects_what_it_does_not_understand(tmp_path):
+    """No reference files needed: a MAT-v5 header is not v7.3, and a file without an HDF5 signature or with a newer
+    superblock version raises Hdf5Error instead of returning garbage."""
+    from krylov_robustness_b200.hdf5_min import Hdf5Error, is_v73, loadmat73
+    import scipy.io as sio
+    v5 = tmp_path / "v5.mat"
+    sio.savemat(str(v5), {"A": sp.identity(3, format="csc")})
+    assert not is_v73(str(v5))
+    bad = tmp_path / "bad.mat"
+    bad.write_bytes(b"MATLAB 7.3 MAT-file, Platform: none".ljust(512, b" ") + b"not hdf5 at all" * 10)
+    assert is_v73(str(bad))
+    with pytest.raises(Hdf5Error, match="signature"):
+        loadmat73(str(bad))
+    newer = tmp_path / "newer.mat"
+    newer.write_bytes(b"MATLAB 7.3 MAT-file".ljust(512, b" ") + b"\x89HDF\r\n\x1a\n" + bytes([2]) + b"\0" * 64)
+    with pytest.raises(Hdf5Error, match="superblock version 2"):
+        loadmat73(str(newer))
