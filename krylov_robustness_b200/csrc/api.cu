@@ -17,6 +17,7 @@
 #include "vecops.cuh"
 #include "blockkrylov.cuh"
 #include "entries.cuh"
+#include "entries_local.cuh"
 #include "frechet.cuh"
 #include "mctrace.cuh"
 #include "nodepairs.cuh"

@@ -132,21 +132,16 @@ __global__ void entries_init_kernel(double* __restrict__ V0, int64_t n, const in
     V0[(int64_t)(c / PW) * n * PW + (rows[c] - 1) * PW + (c % PW)] = 1.0;
 }
 
-// One CTA per distinct row index: x = f(Hsym) e1 for the jj x jj projection (jj = j+1 steps done,
-// 1-based step number), lag-3 stopping test on ||x - pad(x_{jj-3})||_2 (function_multiple_entries.m:121-151).
-// hist[col][4][it1]: ring of the last first-columns; xfin[col][it1] + nfin[col]: frozen at convergence.
-__global__ void __launch_bounds__(JAC_THREADS)
-entries_step_kernel(const double* __restrict__ Hc, int it1, int jj, int fun, double tol, double* __restrict__ hist,
-                    double* __restrict__ xfin, int* __restrict__ nfin, int* __restrict__ conv, int* __restrict__ nactive) {
-    extern __shared__ double dyn[];
-    __shared__ JacobiShared sh;
-    const int c = blockIdx.x;
-    if (conv[c]) return;
+// x = f(Hsym) e1 for the jj x jj projection (jj = j+1 steps done, 1-based step number) and the lag-3 stopping test on
+// ||x - pad(x_{jj-3})||_2 (function_multiple_entries.m:121-151).  Called by all JAC_THREADS threads of a CTA.
+// H: columns of the Hessenberg matrix, column cc at H + cc*(it1+1); hc: ring of the last four first-columns [4][it1];
+// dyn: scratch of 2*jj*(jj|1) + jj doubles.  Leaves x in dyn + 2*jj*(jj|1), stores it in the ring, returns "converged".
+__device__ __forceinline__ bool entries_project_step(const double* H, int it1, int jj, int fun, double tol, double* hc,
+                                                     double* dyn, JacobiShared* sh) {
     const int lda = jj | 1;
     double* A = dyn;
     double* V = A + jj * lda;
     double* x = V + jj * lda;
-    const double* H = Hc + (int64_t)c * it1 * (it1 + 1);
     for (int e = threadIdx.x; e < jj * jj; e += JAC_THREADS) {
         int r = e % jj, cc = e / jj;
         // H(r, cc) is stored in column cc at index r (valid for r <= cc + 1)
@@ -156,14 +151,13 @@ entries_step_kernel(const double* __restrict__ Hc, int it1, int jj, int fun, dou
         V[r + cc * lda] = r == cc ? 1.0 : 0.0;
     }
     __syncthreads();
-    block_jacobi(A, jj, lda, V, lda, &sh);
+    block_jacobi(A, jj, lda, V, lda, sh);
     for (int i = threadIdx.x; i < jj; i += JAC_THREADS) {
         double s = 0.0;
         for (int k = 0; k < jj; ++k) s += V[i + k * lda] * fun_eval(fun, A[k + k * lda]) * V[0 + k * lda];
         x[i] = s;
     }
     __syncthreads();
-    double* hc = hist + (int64_t)c * 4 * it1;
     double err2 = 0.0;
     if (jj > 3) {
         const double* old = hc + (int64_t)((jj - 3) & 3) * it1;      // first column of step jj-3 (size jj-3)
@@ -172,14 +166,26 @@ entries_step_kernel(const double* __restrict__ Hc, int it1, int jj, int fun, dou
             err2 += d * d;
         }
     }
-    err2 = block_sum(err2, sh.red);
-    for (int i = threadIdx.x; i < jj; i += JAC_THREADS) {
-        hc[(int64_t)(jj & 3) * it1 + i] = x[i];
-        xfin[(int64_t)c * it1 + i] = x[i];
-    }
+    err2 = block_sum(err2, sh->red);
+    for (int i = threadIdx.x; i < jj; i += JAC_THREADS) hc[(int64_t)(jj & 3) * it1 + i] = x[i];
+    return jj > 3 && !(sqrt(err2) > tol);
+}
+
+// One CTA per distinct row index.  hist[col][4][it1]: ring of the last first-columns; xfin[col][it1] + nfin[col]:
+// frozen at convergence.
+__global__ void __launch_bounds__(JAC_THREADS)
+entries_step_kernel(const double* __restrict__ Hc, int it1, int jj, int fun, double tol, double* __restrict__ hist,
+                    double* __restrict__ xfin, int* __restrict__ nfin, int* __restrict__ conv, int* __restrict__ nactive) {
+    extern __shared__ double dyn[];
+    __shared__ JacobiShared sh;
+    const int c = blockIdx.x;
+    if (conv[c]) return;
+    const double* x = dyn + 2 * jj * (jj | 1);
+    const bool done = entries_project_step(Hc + (int64_t)c * it1 * (it1 + 1), it1, jj, fun, tol, hist + (int64_t)c * 4 * it1, dyn, &sh);
+    for (int i = threadIdx.x; i < jj; i += JAC_THREADS) xfin[(int64_t)c * it1 + i] = x[i];
     if (threadIdx.x == 0) {
         nfin[c] = jj;
-        if (jj > 3 && !(sqrt(err2) > tol)) {
+        if (done) {
             conv[c] = 1;
             atomicSub(nactive, 1);
         }

@@ -1,0 +1,295 @@
+// entries_local.cuh - function_multiple_entries (functions/function_multiple_entries.m:86-164) on graphs whose Krylov
+// vectors stay LOCAL: the j-th basis vector of K(A, e_h) lives on the nodes within j hops of h, and on a road network
+// (config C2: datasets_paper/Transport, degree 2-3) sixteen hops reach a few hundred of the 10^5 nodes.  The dense
+// batch of entries.cuh streams n rows per column per pass for them; here ONE CTA runs the whole Arnoldi process of a
+// column in shared memory on the ball around h:
+//   * the ball grows one BFS level per step (hash table global id -> local index; a new level is sorted by global id,
+//     so the local numbering - and with it every summation order - is deterministic),
+//   * local index order = BFS order, so basis vector l is stored with |ball(l)| entries only (a triangular arena),
+//   * w = A v_j by rows in stored CSR order, CGS2 + the third pass of arnoldi_krylov.m:104-106 (all inner products of
+//     a pass before its update, as the reference), the projected solve + lag-3 stop of entries_project_step,
+//   * the requested entries f(A)(h, j2) = sum_l V_l(j2) x_l straight from the arena.
+// Columns are handed out by a ticket counter.  A column whose ball outgrows the CTA's budget (or that has not stopped
+// after IT_LOC steps while the caller allows more) is flagged and goes through the dense batch: results do not depend
+// on which path a column took beyond rounding (test_gpu_krylov.py::test_function_multiple_entries_local_vs_dense).
+// Needs a symmetric stored pattern (w's support is found from the rows of v's support) and no pending edge edits.
+#pragma once
+#include "entries.cuh"
+
+namespace kr {
+
+constexpr int EL_MAXN = 1024;        // nodes of a ball
+constexpr int EL_HCAP = 2048;        // hash slots (power of two, load <= 1/2)
+constexpr int EL_ARENA = 6144;       // doubles of basis storage: sum over l of |ball(l)|
+constexpr int EL_IT = 24;            // steps a column may take on this path
+
+struct EntriesLocalArgs {
+    const int64_t* rows;             // [R] 1-based start nodes
+    const int* pair_begin;           // [R + 1] pairs of column c: pair_list[pair_begin[c] .. pair_begin[c+1])
+    const int* pair_list;            // pair numbers sorted by column
+    const int64_t* j2;               // [k] 1-based second index of every pair
+    double* X;                       // [k]
+    int* steps;                      // [R] steps taken (reference's per-space iteration count)
+    int* flag;                       // [R] 1 = not handled here
+    int* ticket;
+    int R, itl, it_is_cap, fun;      // itl = min(it, EL_IT); it_is_cap: it <= EL_IT (running out of steps is final)
+    double tol;
+};
+
+static_assert(EL_HCAP == 2048 && EL_HCAP >= 2 * EL_MAXN - 0 && EL_MAXN + JAC_THREADS < EL_HCAP, "hash sized for the ball");
+__device__ __forceinline__ unsigned el_hash(int g) { return ((unsigned)g * 2654435761u) >> 21; }   // 11 bits
+
+__device__ __forceinline__ int el_lookup(const int* keys, const int* vals, int g) {
+    unsigned s = el_hash(g);
+    for (;;) {
+        const int k = keys[s];
+        if (k == g) return vals[s];
+        if (k == -1) return -1;
+        s = (s + 1) & (EL_HCAP - 1);
+    }
+}
+
+__global__ void __launch_bounds__(JAC_THREADS)
+entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
+    extern __shared__ double dyn[];
+    __shared__ JacobiShared sh;
+    __shared__ int s_col, s_m, s_over;
+    __shared__ int off[EL_IT + 2], len[EL_IT + 2];
+    __shared__ double hcoef[EL_IT + 1];
+    __shared__ double s_r;
+    const int it1 = a.itl + 1;
+    double* arena = dyn;
+    double* Hl = arena + EL_ARENA;                        // it1 columns of it1 + 1
+    double* ring = Hl + it1 * (it1 + 1);                  // 4 x it1
+    double* scratch = ring + 4 * it1;                     // 2 jj (jj|1) + jj for jj <= itl
+    int* keys = reinterpret_cast<int*>(scratch + 2 * a.itl * (a.itl | 1) + a.itl);
+    int* vals = keys + EL_HCAP;
+    int* L = vals + EL_HCAP;                              // global ids in local order
+    int* rs = L + EL_MAXN;                                // first stored nonzero of the node's row
+    int* rl = rs + EL_MAXN;                               // its length (also the sort buffer of a new level)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = JAC_THREADS / 32;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_col = atomicAdd(a.ticket, 1);
+        __syncthreads();
+        const int c = s_col;
+        if (c >= a.R) return;
+        // ---- reset
+        for (int i = tid; i < EL_HCAP; i += JAC_THREADS) keys[i] = -1;
+        for (int i = tid; i < it1 * (it1 + 1); i += JAC_THREADS) Hl[i] = 0.0;
+        for (int i = tid; i < 4 * it1; i += JAC_THREADS) ring[i] = 0.0;
+        __syncthreads();
+        const int h0 = (int)(a.rows[c] - 1);
+        if (tid == 0) {
+            const unsigned s = el_hash(h0);
+            keys[s] = h0;
+            vals[s] = 0;
+            L[0] = h0;
+            const int sp = A.row_pos[h0];
+            rs[0] = A.row_ptr[sp];
+            rl[0] = A.row_ptr[sp + 1] - rs[0];
+            s_m = 1;
+            s_over = 0;
+            off[0] = 0;
+            len[0] = 1;
+            arena[0] = 1.0;
+        }
+        __syncthreads();
+        int nsteps = 0;
+        bool over = false, done = false;
+        int lev_begin = 0;                                 // first local index of the newest BFS level
+        for (int j = 0; j < a.itl; ++j) {
+            // ---- next BFS level: neighbours of level j that are not in the ball yet
+            const int m_old = s_m;
+            __syncthreads();
+            for (int idx = lev_begin + tid; idx < m_old; idx += JAC_THREADS) {
+                const int p0 = rs[idx], p1 = p0 + rl[idx];
+                for (int p = p0; p < p1; ++p) {
+                    // a full ball stops the insertions at once (the table must never fill up: hub rows)
+                    if (*(volatile int*)&s_m >= EL_MAXN) { s_over = 1; break; }
+                    const int g = A.col[p];
+                    unsigned s = el_hash(g);
+                    for (;;) {
+                        const int k = atomicCAS(&keys[s], -1, g);
+                        if (k == -1) {
+                            const int t = atomicAdd(&s_m, 1);
+                            if (t < EL_MAXN) L[t] = g; else s_over = 1;
+                            break;
+                        }
+                        if (k == g) break;
+                        s = (s + 1) & (EL_HCAP - 1);
+                    }
+                }
+            }
+            __syncthreads();
+            const int m = s_m;
+            if (s_over || off[j] + len[j] + m > EL_ARENA) { over = true; break; }
+            // ---- sort the new level by global id (rank sort; a level has tens of nodes), then index it
+            const int nnew = m - m_old;
+            for (int i = tid; i < nnew; i += JAC_THREADS) {
+                const int g = L[m_old + i];
+                int rank = 0;
+                for (int q = 0; q < nnew; ++q) rank += L[m_old + q] < g;
+                rl[m_old + rank] = g;
+            }
+            __syncthreads();
+            for (int i = m_old + tid; i < m; i += JAC_THREADS) {
+                const int g = rl[i];
+                L[i] = g;
+                unsigned s = el_hash(g);
+                while (keys[s] != g) s = (s + 1) & (EL_HCAP - 1);
+                vals[s] = i;
+                const int sp = A.row_pos[g];
+                rs[i] = A.row_ptr[sp];
+            }
+            __syncthreads();
+            for (int i = m_old + tid; i < m; i += JAC_THREADS) rl[i] = A.row_ptr[A.row_pos[L[i]] + 1] - rs[i];
+            if (tid == 0) {
+                off[j + 1] = off[j] + len[j];
+                len[j + 1] = m;
+            }
+            __syncthreads();
+            lev_begin = m_old;
+            // ---- w = A v_j on the ball (rows in stored order; v_j is zero beyond len[j])
+            const double* vj = arena + off[j];
+            const int lj = len[j];
+            double* w = arena + off[j + 1];
+            for (int r = tid; r < m; r += JAC_THREADS) {
+                const int p0 = rs[r], p1 = p0 + rl[r];
+                double s = 0.0;
+                for (int p = p0; p < p1; ++p) {
+                    const int li = el_lookup(keys, vals, A.col[p]);
+                    if (li >= 0 && li < lj) s += (A.val ? A.val[p] : A.uval) * vj[li];
+                }
+                w[r] = s;
+            }
+            __syncthreads();
+            // ---- CGS2 + third pass against V_0..V_j (arnoldi_krylov.m:104-106, :119-125)
+            double* Hcol = Hl + j * (it1 + 1);
+            for (int pass = 0; pass < 3; ++pass) {
+                for (int l = warp; l <= j; l += NW) {
+                    const double* vl = arena + off[l];
+                    const int ll = len[l];
+                    double s = 0.0;
+                    for (int i = lane; i < ll; i += 32) s += vl[i] * w[i];
+                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0) hcoef[l] = s;
+                }
+                __syncthreads();
+                for (int i = tid; i < m; i += JAC_THREADS) {
+                    double x = w[i];
+                    for (int l = 0; l <= j; ++l)
+                        if (i < len[l]) x -= hcoef[l] * arena[off[l] + i];
+                    w[i] = x;
+                }
+                if (tid <= j) {
+                    if (pass == 0) Hcol[tid] = hcoef[tid];
+                    else if (pass == 1) Hcol[tid] += hcoef[tid];
+                    else Hcol[tid] += hcoef[tid] * s_r;
+                }
+                __syncthreads();
+                if (pass == 1) {
+                    double s = 0.0;
+                    for (int i = tid; i < m; i += JAC_THREADS) s += w[i] * w[i];
+                    s = block_sum(s, sh.red);
+                    const double r = sqrt(s);
+                    const double inv = r > 0.0 ? 1.0 / r : 0.0;
+                    for (int i = tid; i < m; i += JAC_THREADS) w[i] *= inv;
+                    if (tid == 0) {
+                        s_r = r;
+                        Hcol[j + 1] = r;
+                    }
+                    __syncthreads();
+                }
+            }
+            // ---- projected problem and stopping test
+            const int jj = j + 1;
+            done = entries_project_step(Hl, it1, jj, a.fun, a.tol, ring, scratch, &sh);
+            nsteps = jj;
+            __syncthreads();
+            if (done) break;
+        }
+        if (over || (!done && !a.it_is_cap)) {
+            if (tid == 0) { a.flag[c] = 1; a.steps[c] = 0; }
+            continue;
+        }
+        // ---- entries: X[p] = sum_{l < nsteps} V_l(j2) x_l     (function_multiple_entries.m:162-164)
+        const double* x = scratch + 2 * nsteps * (nsteps | 1);
+        for (int q = a.pair_begin[c] + tid; q < a.pair_begin[c + 1]; q += JAC_THREADS) {
+            const int p = a.pair_list[q];
+            const int li = el_lookup(keys, vals, (int)(a.j2[p] - 1));
+            double s = 0.0;
+            if (li >= 0)
+                for (int l = 0; l < nsteps; ++l)
+                    if (li < len[l]) s += arena[off[l] + li] * x[l];
+            a.X[p] = s;
+        }
+        if (tid == 0) { a.flag[c] = 0; a.steps[c] = nsteps; }
+    }
+}
+
+struct EntriesLocalResult {
+    std::vector<double> X;           // [k], valid where flag[colof[p]] == 0
+    std::vector<int> steps, flag;    // [R]
+};
+
+inline size_t entries_local_smem(int itl) {
+    const int it1 = itl + 1;
+    return (size_t)(EL_ARENA + it1 * (it1 + 1) + 4 * it1 + 2 * itl * (itl | 1) + itl) * sizeof(double) +
+           (size_t)(2 * EL_HCAP + 3 * EL_MAXN) * sizeof(int);
+}
+
+// rows: distinct first indices (1-based); colof[p]: column of pair p; j2[p]: second index (1-based)
+inline EntriesLocalResult entries_local_run(kr_ctx* ctx, const kr_matrix* M, const std::vector<int64_t>& rows,
+                                            const std::vector<int>& colof, const std::vector<int64_t>& j2, int fun,
+                                            double tol, int it) {
+    const int R = (int)rows.size(), k = (int)colof.size();
+    EntriesLocalResult out;
+    std::vector<int> pb(R + 1, 0), pl(k);
+    for (int p = 0; p < k; ++p) pb[colof[p] + 1]++;
+    for (int c = 0; c < R; ++c) pb[c + 1] += pb[c];
+    {
+        std::vector<int> next(pb.begin(), pb.end() - 1);
+        for (int p = 0; p < k; ++p) pl[next[colof[p]]++] = p;
+    }
+    DevBuf<int64_t> drows(ctx, R), dj2(ctx, k);
+    DevBuf<int> dpb(ctx, R + 1), dpl(ctx, k), dstate(ctx, (size_t)2 * R + 1);
+    DevBuf<double> dX(ctx, k);
+    drows.upload(rows.data(), R);
+    dj2.upload(j2.data(), k);
+    dpb.upload(pb.data(), R + 1);
+    dpl.upload(pl.data(), k);
+    dstate.zero();
+    dX.zero();
+    EntriesLocalArgs a;
+    a.rows = drows.p;
+    a.pair_begin = dpb.p;
+    a.pair_list = dpl.p;
+    a.j2 = dj2.p;
+    a.X = dX.p;
+    a.steps = dstate.p;
+    a.flag = dstate.p + R;
+    a.ticket = dstate.p + 2 * R;
+    a.R = R;
+    a.itl = std::min(it, EL_IT);
+    a.it_is_cap = it <= EL_IT;
+    a.fun = fun;
+    a.tol = tol;
+    const size_t smem = entries_local_smem(a.itl);
+    static bool attr_set[64] = {};
+    if (first_use_on_device(attr_set, ctx->device))
+        KR_CUDA(cudaFuncSetAttribute(entries_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)entries_local_smem(EL_IT)));
+    const int per_sm = std::max(1, (int)((size_t)220 * 1024 / (smem + 2048)));
+    const int ctas = (int)std::min<int64_t>(R, (int64_t)ctx->num_sms * per_sm);
+    KR_LAUNCH(ctx, entries_local_kernel, ctas, JAC_THREADS, smem, M->dev.view(), a);
+    out.X = dX.to_host();
+    std::vector<int> st = dstate.to_host();
+    out.steps.assign(st.begin(), st.begin() + R);
+    out.flag.assign(st.begin() + R, st.begin() + 2 * R);
+    return out;
+}
+
+}  // namespace kr

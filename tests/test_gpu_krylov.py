@@ -305,6 +305,54 @@ def test_function_multiple_entries_vs_oracle(kr, O, graphs, gname, fun):
     assert np.max(np.abs(X - oX)) <= RTOL * np.max(np.abs(oX))
 
 
+@pytest.mark.parametrize("gname,fun,npairs", [("transport_Vermont", "cosh", 400), ("transport_Rome", "exp", 120),
+                                              ("grid_England", "sinh", 60)])
+def test_function_multiple_entries_local_vs_dense(kr, O, graphs, monkeypatch, gname, fun, npairs):
+    """Spaces whose vectors stay on a small ball around the start node run whole in one CTA (csrc/entries_local.cuh);
+    the others (ball or step budget exceeded) take the dense batch.  Both orders of arithmetic follow
+    arnoldi_krylov.m:104-106, so the entries agree to rounding, the iteration count exactly, and the oracle to 1e-10.
+    On the road network every space is local: no SpMM launch at all."""
+    A = graphs(gname).astype(np.float64)
+    A = (A / A.max()).tocsr()
+    n = A.shape[0]
+    f = {"exp": np.exp, "sinh": np.sinh, "cosh": np.cosh}[fun]
+    nrm, _ = O.normest(A, 1e-2)
+    tol = 1e-8 * float(f(nrm))
+    L = sp.tril(A, -1).tocoo()
+    rng = np.random.default_rng(17)
+    sel = rng.choice(L.nnz, min(npairs, L.nnz), replace=False)
+    om = np.stack([L.row[sel] + 1, L.col[sel] + 1], 1).astype(np.int64)
+    om[3] = [om[3, 0], om[3, 0]]                                  # a diagonal entry
+    om[4] = [om[0, 0], int(rng.integers(1, n + 1))]               # a far-away second index (zero unless reached)
+    ctx = kr.Context.default()
+    M = kr.Matrix(A, ctx)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c0 = ctx.counters()
+        X1, it1 = kr.function_multiple_entries(M, om, fun, tol, 100)
+        c1 = ctx.counters()
+        monkeypatch.setenv("KR_ENTRIES_LOCAL", "0")
+        X0, it0 = kr.function_multiple_entries(M, om, fun, tol, 100)
+        c2 = ctx.counters()
+        monkeypatch.delenv("KR_ENTRIES_LOCAL")
+        oX, oit = O.function_multiple_entries(A, om[:10], fun, tol, 100)
+    scale = np.max(np.abs(X0))
+    assert it1 == it0
+    assert np.max(np.abs(X1 - X0)) <= 1e-12 * scale
+    assert np.max(np.abs(X1[:10] - oX)) <= RTOL * max(np.max(np.abs(oX)), 1e-300)
+    assert c2["spmm_launches"] - c1["spmm_launches"] > 0                                      # the dense batch launches SpMMs
+    if gname == "transport_Vermont":
+        assert c1["spmm_launches"] - c0["spmm_launches"] == 0                                 # every space was local
+    # an iteration cap below the stopping step is final on both paths
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Xa, ita = kr.function_multiple_entries(M, om[:40], fun, tol, 5)
+        monkeypatch.setenv("KR_ENTRIES_LOCAL", "0")
+        Xb, itb = kr.function_multiple_entries(M, om[:40], fun, tol, 5)
+    assert ita == itb == 5
+    assert np.max(np.abs(Xa - Xb)) <= 1e-12 * scale
+
+
 def test_function_multiple_entries_chunked_rows(kr, O, graphs, monkeypatch):
     """Distinct row indices are processed in chunks on the device; forcing tiny chunks must not change
     a single bit of the entries (every space is independent)."""
