@@ -132,6 +132,22 @@ __global__ void entries_init_kernel(double* __restrict__ V0, int64_t n, const in
     V0[(int64_t)(c / PW) * n * PW + (rows[c] - 1) * PW + (c % PW)] = 1.0;
 }
 
+// lag-3 stopping test on ||x - pad(x_{jj-3})||_2 (function_multiple_entries.m:121-151) for the first column x of step jj;
+// hc: ring of the last four first-columns [4][it1], x is stored in it.  Called by all JAC_THREADS threads of a CTA.
+__device__ __forceinline__ bool entries_stop_test(const double* x, int it1, int jj, double tol, double* hc, JacobiShared* sh) {
+    double err2 = 0.0;
+    if (jj > 3) {
+        const double* old = hc + (int64_t)((jj - 3) & 3) * it1;      // first column of step jj-3 (size jj-3)
+        for (int i = threadIdx.x; i < jj; i += JAC_THREADS) {
+            double d = x[i] - (i < jj - 3 ? old[i] : 0.0);
+            err2 += d * d;
+        }
+    }
+    err2 = block_sum(err2, sh->red);
+    for (int i = threadIdx.x; i < jj; i += JAC_THREADS) hc[(int64_t)(jj & 3) * it1 + i] = x[i];
+    return jj > 3 && !(sqrt(err2) > tol);
+}
+
 // x = f(Hsym) e1 for the jj x jj projection (jj = j+1 steps done, 1-based step number) and the lag-3 stopping test on
 // ||x - pad(x_{jj-3})||_2 (function_multiple_entries.m:121-151).  Called by all JAC_THREADS threads of a CTA.
 // H: columns of the Hessenberg matrix, column cc at H + cc*(it1+1); hc: ring of the last four first-columns [4][it1];
@@ -158,17 +174,7 @@ __device__ __forceinline__ bool entries_project_step(const double* H, int it1, i
         x[i] = s;
     }
     __syncthreads();
-    double err2 = 0.0;
-    if (jj > 3) {
-        const double* old = hc + (int64_t)((jj - 3) & 3) * it1;      // first column of step jj-3 (size jj-3)
-        for (int i = threadIdx.x; i < jj; i += JAC_THREADS) {
-            double d = x[i] - (i < jj - 3 ? old[i] : 0.0);
-            err2 += d * d;
-        }
-    }
-    err2 = block_sum(err2, sh->red);
-    for (int i = threadIdx.x; i < jj; i += JAC_THREADS) hc[(int64_t)(jj & 3) * it1 + i] = x[i];
-    return jj > 3 && !(sqrt(err2) > tol);
+    return entries_stop_test(x, it1, jj, tol, hc, sh);
 }
 
 // One CTA per distinct row index.  hist[col][4][it1]: ring of the last first-columns; xfin[col][it1] + nfin[col]:

@@ -18,9 +18,9 @@
 
 namespace kr {
 
-constexpr int EL_MAXN = 1024;        // nodes of a ball
+constexpr int EL_MAXN = 768;         // nodes of a ball
 constexpr int EL_HCAP = 2048;        // hash slots (power of two, load <= 1/2)
-constexpr int EL_ARENA = 6144;       // doubles of basis storage: sum over l of |ball(l)|
+constexpr int EL_ARENA = 4096;       // doubles of basis storage: sum over l of |ball(l)| (three CTAs per SM)
 constexpr int EL_IT = 24;            // steps a column may take on this path
 
 struct EntriesLocalArgs {
@@ -33,6 +33,7 @@ struct EntriesLocalArgs {
     int* flag;                       // [R] 1 = not handled here
     int* ticket;
     int R, itl, it_is_cap, fun;      // itl = min(it, EL_IT); it_is_cap: it <= EL_IT (running out of steps is final)
+    int use_ql;                      // projected solve: 1 = tridiagonal QL by one warp, 0 = the dense path's Jacobi
     double tol;
 };
 
@@ -49,6 +50,92 @@ __device__ __forceinline__ int el_lookup(const int* keys, const int* vals, int g
     }
 }
 
+__host__ __device__ inline int el_scratch_doubles(int itl, int use_ql) {
+    return use_ql ? itl * (EL_IT + 1) + itl : 2 * itl * (itl | 1) + itl;
+}
+constexpr int EL_LDQ = EL_IT + 1;   // odd: the lanes' rows of Q fall into different banks
+static_assert(EL_IT <= 32 && (EL_LDQ & 1) == 1, "one lane per row of Q");
+
+// x = f(T) e1 for the symmetric tridiagonal part T of the projection (diagonal H(i,i), off-diagonal the mean of H(i+1,i)
+// and H(i,i+1)): implicit QL with eigenvector accumulation (EISPACK tql2) run by ONE warp without any barrier - every
+// lane carries the scalar recurrence redundantly in private copies of d / e, lane k owns row k of Q.  With full
+// re-orthogonalisation on a symmetric A the entries of H outside the band are rounding noise (1e-16 ||A||), so this equals
+// the dense path's Jacobi solve of (H + H')/2 to rounding; the warp-local form has no CTA barrier per rotation round.
+__device__ __forceinline__ void warp_tridiag_fx(const double* H, int it1, int n, int fun, double* Q, double* x) {
+    const int lane = threadIdx.x & 31;
+    double d[EL_IT], e[EL_IT];
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        d[i] = H[(int64_t)i * (it1 + 1) + i];
+        e[i] = i + 1 < n ? 0.5 * (H[(int64_t)i * (it1 + 1) + i + 1] + H[(int64_t)(i + 1) * (it1 + 1) + i]) : 0.0;
+    }
+    if (lane < n)
+        for (int i = 0; i < n; ++i) Q[lane * EL_LDQ + i] = lane == i ? 1.0 : 0.0;
+    double f = 0.0, tst1 = 0.0;
+    const double eps = 2.220446049250313e-16;
+#pragma unroll 1
+    for (int l = 0; l < n; ++l) {
+        tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+        int m = l;
+        while (m < n) {
+            if (fabs(e[m]) <= eps * tst1) break;
+            ++m;
+        }
+        if (m > l) {
+            int iter = 0;
+            do {
+                ++iter;
+                double g = d[l];
+                double p = (d[l + 1] - g) / (2.0 * e[l]);
+                double r = sqrt(fma(p, p, 1.0));
+                if (p < 0.0) r = -r;
+                d[l] = e[l] / (p + r);
+                d[l + 1] = e[l] * (p + r);
+                const double dl1 = d[l + 1];
+                double h = g - d[l];
+                for (int i = l + 2; i < n; ++i) d[i] -= h;
+                f += h;
+                p = d[m];
+                double c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
+                const double el1 = e[l + 1];
+#pragma unroll 1
+                for (int i = m - 1; i >= l; --i) {
+                    c3 = c2;
+                    c2 = c;
+                    s2 = s;
+                    g = c * e[i];
+                    h = c * p;
+                    // r = |(p, e_i)| and the rotation from one reciprocal square root (entries are O(||A||): no scaling)
+                    const double r2 = fma(p, p, e[i] * e[i]);
+                    const double rinv = rsqrt(r2);
+                    r = r2 * rinv;
+                    e[i + 1] = s * r;
+                    s = e[i] * rinv;
+                    c = p * rinv;
+                    p = c * d[i] - s * g;
+                    d[i + 1] = h + s * (c * g + s * d[i]);
+                    if (lane < n) {
+                        const double q1 = Q[lane * EL_LDQ + i + 1], q0 = Q[lane * EL_LDQ + i];
+                        Q[lane * EL_LDQ + i + 1] = s * q0 + c * q1;
+                        Q[lane * EL_LDQ + i] = c * q0 - s * q1;
+                    }
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                e[l] = s * p;
+                d[l] = c * p;
+            } while (fabs(e[l]) > eps * tst1 && iter < 60);
+        }
+        d[l] += f;
+        e[l] = 0.0;
+    }
+    __syncwarp();
+    if (lane < n) {
+        double sum = 0.0;
+        for (int k = 0; k < n; ++k) sum += Q[lane * EL_LDQ + k] * fun_eval(fun, d[k]) * Q[k];
+        x[lane] = sum;
+    }
+}
+
 __global__ void __launch_bounds__(JAC_THREADS)
 entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
     extern __shared__ double dyn[];
@@ -61,8 +148,8 @@ entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
     double* arena = dyn;
     double* Hl = arena + EL_ARENA;                        // it1 columns of it1 + 1
     double* ring = Hl + it1 * (it1 + 1);                  // 4 x it1
-    double* scratch = ring + 4 * it1;                     // 2 jj (jj|1) + jj for jj <= itl
-    int* keys = reinterpret_cast<int*>(scratch + 2 * a.itl * (a.itl | 1) + a.itl);
+    double* scratch = ring + 4 * it1;                     // Jacobi: 2 jj (jj|1) + jj for jj <= itl; QL: Q (itl x EL_LDQ) + x
+    int* keys = reinterpret_cast<int*>(scratch + el_scratch_doubles(a.itl, a.use_ql));
     int* vals = keys + EL_HCAP;
     int* L = vals + EL_HCAP;                              // global ids in local order
     int* rs = L + EL_MAXN;                                // first stored nonzero of the node's row
@@ -206,7 +293,13 @@ entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
             }
             // ---- projected problem and stopping test
             const int jj = j + 1;
-            done = entries_project_step(Hl, it1, jj, a.fun, a.tol, ring, scratch, &sh);
+            if (a.use_ql) {
+                if (warp == 0) warp_tridiag_fx(Hl, it1, jj, a.fun, scratch, scratch + a.itl * EL_LDQ);
+                __syncthreads();
+                done = entries_stop_test(scratch + a.itl * EL_LDQ, it1, jj, a.tol, ring, &sh);
+            } else {
+                done = entries_project_step(Hl, it1, jj, a.fun, a.tol, ring, scratch, &sh);
+            }
             nsteps = jj;
             __syncthreads();
             if (done) break;
@@ -216,7 +309,7 @@ entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
             continue;
         }
         // ---- entries: X[p] = sum_{l < nsteps} V_l(j2) x_l     (function_multiple_entries.m:162-164)
-        const double* x = scratch + 2 * nsteps * (nsteps | 1);
+        const double* x = a.use_ql ? scratch + a.itl * EL_LDQ : scratch + 2 * nsteps * (nsteps | 1);
         for (int q = a.pair_begin[c] + tid; q < a.pair_begin[c + 1]; q += JAC_THREADS) {
             const int p = a.pair_list[q];
             const int li = el_lookup(keys, vals, (int)(a.j2[p] - 1));
@@ -235,9 +328,9 @@ struct EntriesLocalResult {
     std::vector<int> steps, flag;    // [R]
 };
 
-inline size_t entries_local_smem(int itl) {
+inline size_t entries_local_smem(int itl, int use_ql) {
     const int it1 = itl + 1;
-    return (size_t)(EL_ARENA + it1 * (it1 + 1) + 4 * it1 + 2 * itl * (itl | 1) + itl) * sizeof(double) +
+    return (size_t)(EL_ARENA + it1 * (it1 + 1) + 4 * it1 + el_scratch_doubles(itl, use_ql)) * sizeof(double) +
            (size_t)(2 * EL_HCAP + 3 * EL_MAXN) * sizeof(int);
 }
 
@@ -277,12 +370,14 @@ inline EntriesLocalResult entries_local_run(kr_ctx* ctx, const kr_matrix* M, con
     a.it_is_cap = it <= EL_IT;
     a.fun = fun;
     a.tol = tol;
-    const size_t smem = entries_local_smem(a.itl);
+    a.use_ql = 1;
+    if (const char* e = getenv("KR_ENTRIES_LOCAL_JACOBI")) a.use_ql = atoi(e) == 0;     // A/B switch
+    const size_t smem = entries_local_smem(a.itl, a.use_ql);
     static bool attr_set[64] = {};
     if (first_use_on_device(attr_set, ctx->device))
         KR_CUDA(cudaFuncSetAttribute(entries_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)entries_local_smem(EL_IT)));
-    const int per_sm = std::max(1, (int)((size_t)220 * 1024 / (smem + 2048)));
+                                     (int)std::max(entries_local_smem(EL_IT, 0), entries_local_smem(EL_IT, 1))));
+    const int per_sm = std::max(1, (int)((size_t)228 * 1024 / (smem + 4096 + 1024)));      // + static + the per-CTA reserve
     const int ctas = (int)std::min<int64_t>(R, (int64_t)ctx->num_sms * per_sm);
     KR_LAUNCH(ctx, entries_local_kernel, ctas, JAC_THREADS, smem, M->dev.view(), a);
     out.X = dX.to_host();

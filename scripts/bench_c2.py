@@ -76,7 +76,7 @@ def main():
         calls.append(time.perf_counter() - t0)
     out["entries_call_s_prebuilt_matrix"] = min(calls)
     out["entries_equal_to_gradient_call"] = bool(np.array_equal(-2.0 * v, gr))
-    if os.environ.get("KR_ENTRIES_LOCAL") != "0" and args.graph == "transport_Vermont":
+    if os.environ.get("KR_ENTRIES_LOCAL") != "0" and args.graph == "transport_Vermont" and not os.environ.get("KR_C2_SKIP_DENSE"):
         os.environ["KR_ENTRIES_LOCAL"] = "0"
         t0 = time.perf_counter()
         vd, _ = kr.function_multiple_entries(Mt, Om, "cosh", tol, 100)
