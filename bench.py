@@ -218,6 +218,55 @@ def peak_gbs():
         return 6650.0
 
 
+def bench_c2(kr, ctx):
+    """Config C2 (datasets_paper/Transport, gradient over ALL edges): gr = -2 cosh(A + Delta(X))_Omega on the largest road
+    network of the reference's data (Vermont after the scripts' preprocessing, committed fixture), through
+    function_multiple_entries - one single-vector Krylov space per distinct row index, each run whole in one CTA on the
+    ball around its start node (csrc/entries_local.cuh).  Setup as scripts/bench_c2.py / Tests/test_weighted_sinh_lbfgs.m:52."""
+    import warnings
+    import scipy.sparse as sp
+    path = os.path.join(ROOT, "tests", "golden", "graph_transport_Vermont.npz")
+    if not os.path.exists(path):
+        return {"unavailable": "tests/golden/graph_transport_Vermont.npz not found"}
+    z = np.load(path)
+    n = int(z["n"])
+    A = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n)).astype(np.float64)
+    A = (A / A.max()).tocsr()
+    L = sp.tril(A, -1).tocoo()
+    Om = np.stack([L.row + 1, L.col + 1], 1).astype(np.int64)
+    X = 0.1 * L.data * np.random.default_rng(4).random(L.nnz)
+    D = sp.csr_matrix((X, (Om[:, 0] - 1, Om[:, 1] - 1)), shape=(n, n))
+    At = (A + D + D.T).tocsr()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tol = 1e-8 * float(np.cosh(float(kr.normest(A, 1e-2)[0])))
+        t0 = time.perf_counter()
+        M = kr.Matrix(At, ctx)
+        ctx.sync()
+        t_mat = time.perf_counter() - t0
+        kr.function_multiple_entries(M, Om[:256], "cosh", tol, 100)          # warm-up
+        ctx.sync()
+        times, c0 = [], ctx.counters()
+        for _ in range(3):
+            t0 = time.perf_counter()
+            v, it = kr.function_multiple_entries(M, Om, "cosh", tol, 100)
+            ctx.sync()
+            times.append(time.perf_counter() - t0)
+        c1 = ctx.counters()
+    t = min(times)
+    return {"metric": "gradient_entries_per_sec", "value": Om.shape[0] / t, "unit": "entry/s",
+            "workload": "C2: transport_Vermont (n=%d, %d edges), gradient of trace sinh(A+X) over ALL edges = %d entries of "
+                        "cosh(A+Delta) from %d single-vector Arnoldi spaces (full CGS2 + third pass)"
+                        % (n, Om.shape[0], Om.shape[0], int(np.unique(Om[:, 0]).size)),
+            "call_s": t, "calls_timed": len(times), "iterations": int(it), "matrix_analysis_upload_s": t_mat,
+            "matvecs_per_call": (c1["matvecs"] - c0["matvecs"]) // len(times),
+            "gpu_launches_per_call": (c1["launches"] - c0["launches"]) // len(times),
+            "gradient_checksum": float(np.sum(-2.0 * v)), "max_abs_entry": float(np.max(np.abs(2.0 * v))),
+            "timing": "host clock around kr_function_multiple_entries incl. index upload and result download (resident matrix)",
+            "dense_batch_reference_s": 11.7,
+            "note": "round-2 dense batch (all spaces advanced by n x R SpMMs): 11.5-11.9 s for the same call, see DESIGN.md 6"}
+
+
 def bench_c4(kr, ctx):
     """expmv (Al-Mohy-Higham) on the C4 graph: ms per fused Taylor term and its fraction of the HBM roofline
     (algorithmic bytes 4*nnz [pattern-only CSR] + 4*(n+1) + 32*n*q: read b, write b', read-modify-write f)."""
@@ -466,6 +515,10 @@ def run_ours(args):
     secondary_c4 = None
     if rank == 0 and os.environ.get("KR_BENCH_C4", "1" if world == 1 else "0") != "0":
         secondary_c4 = bench_c4(kr, ctx)
+    # ---- config C2: gradient over all edges of the largest Transport road network (rank 0, N == 1)
+    secondary_c2 = None
+    if rank == 0 and os.environ.get("KR_BENCH_C2", "1" if world == 1 else "0") != "0":
+        secondary_c2 = bench_c2(kr, ctx)
 
     if rank == 0:
         mv_step = k * m * world
@@ -520,7 +573,7 @@ def run_ours(args):
                                     "achieved_tb_per_s": 8.0 * nnz * cols_per_launch / (per_launch_ms * 1e-3) / 1e12,
                                     "microbench_ceiling_tb_per_s": 14.8,
                                     "source": "profiles/r01_l2_gather_microbench.json"}},
-            "secondary": secondary, "secondary_c4": secondary_c4, "strong_scaling": strong,
+            "secondary": secondary, "secondary_c4": secondary_c4, "secondary_c2": secondary_c2, "strong_scaling": strong,
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": "oracle.slq_trace (NumPy/SciPy port of the reference path) on 4 probes x %d steps "
                                        "of the same graph, %.1f s" % (m, cpu_dt)},
