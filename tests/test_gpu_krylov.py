@@ -353,6 +353,40 @@ def test_function_multiple_entries_local_vs_dense(kr, O, graphs, monkeypatch, gn
     assert np.max(np.abs(Xa - Xb)) <= 1e-12 * scale
 
 
+def test_function_multiple_entries_local_small_components(kr, O, monkeypatch):
+    """Start nodes whose component is exhausted after a few steps (lucky breakdown: the new vector is exactly zero), an
+    isolated node, self loops and a pattern-only matrix: the one-CTA path and the dense batch walk through the same
+    arithmetic (inverse norm 0 after the breakdown), and both give the oracle's entries."""
+    blocks = []
+    rng = np.random.default_rng(3)
+    for m in (1, 2, 5, 9, 30):                                   # paths of m nodes; the 1-node block is an isolated node
+        P = sp.diags([np.ones(m - 1), np.ones(m - 1)], [-1, 1], shape=(m, m)) if m > 1 else sp.csr_matrix((1, 1))
+        blocks.append(sp.csr_matrix(P))
+    ring = sp.diags([np.ones(39), np.ones(39)], [-1, 1], shape=(40, 40)).tolil()
+    ring[0, 39] = ring[39, 0] = 1.0
+    ring[7, 7] = 1.0                                             # a self loop
+    blocks.append(sp.csr_matrix(ring))
+    A = sp.block_diag(blocks).tocsr().astype(np.float64)
+    n = A.shape[0]
+    om = np.array([[1, 1], [2, 3], [3, 2], [4, 8], [8, 4], [6, 6], [10, 17], [17, 10], [20, 40], [47, 47], [55, 60],
+                   [60, 55], [55, 5], [87, 48]], dtype=np.int64)
+    assert om.max() <= n
+    for W, tag in ((A, "pattern"), (A.multiply(sp.csr_matrix(np.triu(0.5 + rng.random((n, n))) + np.triu(0.5 + rng.random((n, n)), 1).T)).tocsr(), "weighted")):
+        W = ((W + W.T) * 0.5).tocsr()
+        for fun in ("exp", "cosh"):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                X1, it1 = kr.function_multiple_entries(W, om, fun, 1e-10, 20)
+                monkeypatch.setenv("KR_ENTRIES_LOCAL", "0")
+                X0, it0 = kr.function_multiple_entries(W, om, fun, 1e-10, 20)
+                monkeypatch.delenv("KR_ENTRIES_LOCAL")
+                oX, oit = O.function_multiple_entries(W, om, fun, 1e-10, 20)
+            assert np.all(np.isfinite(X1)), (tag, fun)
+            assert it1 == it0 == oit, (tag, fun, it1, it0, oit)
+            assert np.max(np.abs(X1 - X0)) <= 1e-12 * max(1.0, np.max(np.abs(X0))), (tag, fun)
+            assert np.max(np.abs(X1 - oX)) <= RTOL * max(1.0, np.max(np.abs(oX))), (tag, fun)
+
+
 def test_function_multiple_entries_chunked_rows(kr, O, graphs, monkeypatch):
     """Distinct row indices are processed in chunks on the device; forcing tiny chunks must not change
     a single bit of the entries (every space is independent)."""
