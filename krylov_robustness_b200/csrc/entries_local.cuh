@@ -9,8 +9,9 @@
 //   * w = A v_j by rows in stored CSR order, CGS2 + the third pass of arnoldi_krylov.m:104-106 (all inner products of
 //     a pass before its update, as the reference), the projected solve + lag-3 stop of entries_project_step,
 //   * the requested entries f(A)(h, j2) = sum_l V_l(j2) x_l straight from the arena.
-// Columns are handed out by a ticket counter.  A column whose ball outgrows the CTA's budget (or that has not stopped
-// after IT_LOC steps while the caller allows more) is flagged and goes through the dense batch: results do not depend
+// Columns are handed out by a ticket counter.  A column whose ball outgrows the CTA's budget is flagged and run again with
+// the next budget tier; one that outgrows the last tier (or that has not stopped after EL_IT steps while the caller allows
+// more) goes through the dense batch: results do not depend
 // on which path a column took beyond rounding (test_gpu_krylov.py::test_function_multiple_entries_local_vs_dense).
 // Needs a symmetric stored pattern (w's support is found from the rows of v's support) and no pending edge edits.
 #pragma once
@@ -18,9 +19,12 @@
 
 namespace kr {
 
-constexpr int EL_MAXN = 768;         // nodes of a ball
-constexpr int EL_HCAP = 2048;        // hash slots (power of two, load <= 1/2)
-constexpr int EL_ARENA = 4096;       // doubles of basis storage: sum over l of |ball(l)| (three CTAs per SM)
+// Budget of a CTA: nodes of a ball, hash slots (power of two, > maxn + CTA threads: the table never fills up), doubles of
+// basis storage (sum over l of |ball(l)|).  Two tiers: most spaces of a road network fit the small one (five CTAs per
+// SM); what it flags is run again with the next one (three CTAs per SM, then one); what the last one flags takes the dense batch.
+struct EntriesLocalBudget { int maxn, hcap, arena; };
+constexpr int EL_NTIERS = 3;
+constexpr EntriesLocalBudget EL_TIERS[EL_NTIERS] = {{384, 1024, 2048}, {768, 2048, 4096}, {1536, 4096, 16384}};
 constexpr int EL_IT = 24;            // steps a column may take on this path
 
 struct EntriesLocalArgs {
@@ -30,23 +34,25 @@ struct EntriesLocalArgs {
     const int64_t* j2;               // [k] 1-based second index of every pair
     double* X;                       // [k]
     int* steps;                      // [R] steps taken (reference's per-space iteration count)
-    int* flag;                       // [R] 1 = not handled here
+    int* flag;                       // [R] nonzero = not handled here (1: ball outgrew the budget, 2: step limit of this path)
     int* ticket;
     int R, itl, it_is_cap, fun;      // itl = min(it, EL_IT); it_is_cap: it <= EL_IT (running out of steps is final)
     int use_ql;                      // projected solve: 1 = tridiagonal QL by one warp, 0 = the dense path's Jacobi
+    int maxn, hcap, hshift, arena;   // budget (hshift = 32 - log2 hcap)
+    const int* sel;                  // columns to process (null: all of 0..R-1)
+    int nsel;
     double tol;
 };
 
-static_assert(EL_HCAP == 2048 && EL_HCAP >= 2 * EL_MAXN - 0 && EL_MAXN + JAC_THREADS < EL_HCAP, "hash sized for the ball");
-__device__ __forceinline__ unsigned el_hash(int g) { return ((unsigned)g * 2654435761u) >> 21; }   // 11 bits
+__device__ __forceinline__ unsigned el_hash(int g, int hshift) { return ((unsigned)g * 2654435761u) >> hshift; }
 
-__device__ __forceinline__ int el_lookup(const int* keys, const int* vals, int g) {
-    unsigned s = el_hash(g);
+__device__ __forceinline__ int el_lookup(const int* keys, const int* vals, int g, int hshift, int hmask) {
+    unsigned s = el_hash(g, hshift);
     for (;;) {
         const int k = keys[s];
         if (k == g) return vals[s];
         if (k == -1) return -1;
-        s = (s + 1) & (EL_HCAP - 1);
+        s = (s + 1) & hmask;
     }
 }
 
@@ -146,31 +152,32 @@ entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
     __shared__ double s_r;
     const int it1 = a.itl + 1;
     double* arena = dyn;
-    double* Hl = arena + EL_ARENA;                        // it1 columns of it1 + 1
+    double* Hl = arena + a.arena;                        // it1 columns of it1 + 1
     double* ring = Hl + it1 * (it1 + 1);                  // 4 x it1
     double* scratch = ring + 4 * it1;                     // Jacobi: 2 jj (jj|1) + jj for jj <= itl; QL: Q (itl x EL_LDQ) + x
     int* keys = reinterpret_cast<int*>(scratch + el_scratch_doubles(a.itl, a.use_ql));
-    int* vals = keys + EL_HCAP;
-    int* L = vals + EL_HCAP;                              // global ids in local order
-    int* rs = L + EL_MAXN;                                // first stored nonzero of the node's row
-    int* rl = rs + EL_MAXN;                               // its length (also the sort buffer of a new level)
+    int* vals = keys + a.hcap;
+    int* L = vals + a.hcap;                              // global ids in local order
+    int* rs = L + a.maxn;                                // first stored nonzero of the node's row
+    int* rl = rs + a.maxn;                               // its length (also the sort buffer of a new level)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = JAC_THREADS / 32;
+    const int hmask = a.hcap - 1;
 
     for (;;) {
         __syncthreads();
         if (tid == 0) s_col = atomicAdd(a.ticket, 1);
         __syncthreads();
-        const int c = s_col;
-        if (c >= a.R) return;
+        if (s_col >= (a.sel ? a.nsel : a.R)) return;
+        const int c = a.sel ? a.sel[s_col] : s_col;
         // ---- reset
-        for (int i = tid; i < EL_HCAP; i += JAC_THREADS) keys[i] = -1;
+        for (int i = tid; i < a.hcap; i += JAC_THREADS) keys[i] = -1;
         for (int i = tid; i < it1 * (it1 + 1); i += JAC_THREADS) Hl[i] = 0.0;
         for (int i = tid; i < 4 * it1; i += JAC_THREADS) ring[i] = 0.0;
         __syncthreads();
         const int h0 = (int)(a.rows[c] - 1);
         if (tid == 0) {
-            const unsigned s = el_hash(h0);
+            const unsigned s = el_hash(h0, a.hshift);
             keys[s] = h0;
             vals[s] = 0;
             L[0] = h0;
@@ -195,24 +202,24 @@ entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
                 const int p0 = rs[idx], p1 = p0 + rl[idx];
                 for (int p = p0; p < p1; ++p) {
                     // a full ball stops the insertions at once (the table must never fill up: hub rows)
-                    if (*(volatile int*)&s_m >= EL_MAXN) { s_over = 1; break; }
+                    if (*(volatile int*)&s_m >= a.maxn) { s_over = 1; break; }
                     const int g = A.col[p];
-                    unsigned s = el_hash(g);
+                    unsigned s = el_hash(g, a.hshift);
                     for (;;) {
                         const int k = atomicCAS(&keys[s], -1, g);
                         if (k == -1) {
                             const int t = atomicAdd(&s_m, 1);
-                            if (t < EL_MAXN) L[t] = g; else s_over = 1;
+                            if (t < a.maxn) L[t] = g; else s_over = 1;
                             break;
                         }
                         if (k == g) break;
-                        s = (s + 1) & (EL_HCAP - 1);
+                        s = (s + 1) & hmask;
                     }
                 }
             }
             __syncthreads();
             const int m = s_m;
-            if (s_over || off[j] + len[j] + m > EL_ARENA) { over = true; break; }
+            if (s_over || off[j] + len[j] + m > a.arena) { over = true; break; }
             // ---- sort the new level by global id (rank sort; a level has tens of nodes), then index it
             const int nnew = m - m_old;
             for (int i = tid; i < nnew; i += JAC_THREADS) {
@@ -225,8 +232,8 @@ entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
             for (int i = m_old + tid; i < m; i += JAC_THREADS) {
                 const int g = rl[i];
                 L[i] = g;
-                unsigned s = el_hash(g);
-                while (keys[s] != g) s = (s + 1) & (EL_HCAP - 1);
+                unsigned s = el_hash(g, a.hshift);
+                while (keys[s] != g) s = (s + 1) & hmask;
                 vals[s] = i;
                 const int sp = A.row_pos[g];
                 rs[i] = A.row_ptr[sp];
@@ -247,7 +254,7 @@ entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
                 const int p0 = rs[r], p1 = p0 + rl[r];
                 double s = 0.0;
                 for (int p = p0; p < p1; ++p) {
-                    const int li = el_lookup(keys, vals, A.col[p]);
+                    const int li = el_lookup(keys, vals, A.col[p], a.hshift, hmask);
                     if (li >= 0 && li < lj) s += (A.val ? A.val[p] : A.uval) * vj[li];
                 }
                 w[r] = s;
@@ -305,14 +312,14 @@ entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
             if (done) break;
         }
         if (over || (!done && !a.it_is_cap)) {
-            if (tid == 0) { a.flag[c] = 1; a.steps[c] = 0; }
+            if (tid == 0) { a.flag[c] = over ? 1 : 2; a.steps[c] = 0; }     // 1: a larger budget may do, 2: needs more steps
             continue;
         }
         // ---- entries: X[p] = sum_{l < nsteps} V_l(j2) x_l     (function_multiple_entries.m:162-164)
         const double* x = a.use_ql ? scratch + a.itl * EL_LDQ : scratch + 2 * nsteps * (nsteps | 1);
         for (int q = a.pair_begin[c] + tid; q < a.pair_begin[c + 1]; q += JAC_THREADS) {
             const int p = a.pair_list[q];
-            const int li = el_lookup(keys, vals, (int)(a.j2[p] - 1));
+            const int li = el_lookup(keys, vals, (int)(a.j2[p] - 1), a.hshift, hmask);
             double s = 0.0;
             if (li >= 0)
                 for (int l = 0; l < nsteps; ++l)
@@ -328,10 +335,10 @@ struct EntriesLocalResult {
     std::vector<int> steps, flag;    // [R]
 };
 
-inline size_t entries_local_smem(int itl, int use_ql) {
+inline size_t entries_local_smem(int itl, int use_ql, const EntriesLocalBudget& b) {
     const int it1 = itl + 1;
-    return (size_t)(EL_ARENA + it1 * (it1 + 1) + 4 * it1 + el_scratch_doubles(itl, use_ql)) * sizeof(double) +
-           (size_t)(2 * EL_HCAP + 3 * EL_MAXN) * sizeof(int);
+    return (size_t)(b.arena + it1 * (it1 + 1) + 4 * it1 + el_scratch_doubles(itl, use_ql)) * sizeof(double) +
+           (size_t)(2 * b.hcap + 3 * b.maxn) * sizeof(int);
 }
 
 // rows: distinct first indices (1-based); colof[p]: column of pair p; j2[p]: second index (1-based)
@@ -372,14 +379,44 @@ inline EntriesLocalResult entries_local_run(kr_ctx* ctx, const kr_matrix* M, con
     a.tol = tol;
     a.use_ql = 1;
     if (const char* e = getenv("KR_ENTRIES_LOCAL_JACOBI")) a.use_ql = atoi(e) == 0;     // A/B switch
-    const size_t smem = entries_local_smem(a.itl, a.use_ql);
     static bool attr_set[64] = {};
     if (first_use_on_device(attr_set, ctx->device))
         KR_CUDA(cudaFuncSetAttribute(entries_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)std::max(entries_local_smem(EL_IT, 0), entries_local_smem(EL_IT, 1))));
-    const int per_sm = std::max(1, (int)((size_t)228 * 1024 / (smem + 4096 + 1024)));      // + static + the per-CTA reserve
-    const int ctas = (int)std::min<int64_t>(R, (int64_t)ctx->num_sms * per_sm);
-    KR_LAUNCH(ctx, entries_local_kernel, ctas, JAC_THREADS, smem, M->dev.view(), a);
+                                     (int)std::max(entries_local_smem(EL_IT, 0, EL_TIERS[EL_NTIERS - 1]),
+                                                   entries_local_smem(EL_IT, 1, EL_TIERS[EL_NTIERS - 1]))));
+    int first_tier = 0;
+    if (const char* e = getenv("KR_ENTRIES_LOCAL_TIER")) first_tier = std::min(std::max(atoi(e), 0), EL_NTIERS - 1);   // A/B switch
+    DevBuf<int> dsel;
+    std::vector<int> sel;                                   // empty: all columns
+    for (int tier = first_tier; tier < EL_NTIERS; ++tier) {
+        const EntriesLocalBudget& b = EL_TIERS[tier];
+        a.maxn = b.maxn;
+        a.hcap = b.hcap;
+        a.arena = b.arena;
+        a.hshift = 32;
+        for (int h = b.hcap; h > 1; h >>= 1) a.hshift--;
+        if (b.maxn + JAC_THREADS >= b.hcap) fail(KR_ERR_ARG, "entries_local: hash too small for the ball");
+        a.sel = sel.empty() ? nullptr : dsel.p;
+        a.nsel = (int)sel.size();
+        const int todo = sel.empty() ? R : (int)sel.size();
+        const size_t smem = entries_local_smem(a.itl, a.use_ql, b);
+        const int per_sm = std::max(1, (int)((size_t)228 * 1024 / (smem + 4096 + 1024)));      // + static + the per-CTA reserve
+        const int ctas = (int)std::min<int64_t>(todo, (int64_t)ctx->num_sms * per_sm);
+        KR_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(int), ctx->stream));
+        KR_LAUNCH(ctx, entries_local_kernel, ctas, JAC_THREADS, smem, M->dev.view(), a);
+        if (tier == EL_NTIERS - 1) break;
+        // what this tier flagged goes to the next one
+        std::vector<int> fl(R);
+        KR_CUDA(cudaMemcpyAsync(fl.data(), a.flag, (size_t)R * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        KR_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->counters[4] += (int64_t)R * sizeof(int);
+        sel.clear();
+        for (int c = 0; c < R; ++c)
+            if (fl[c] == 1) sel.push_back(c);
+        if (sel.empty()) break;
+        dsel.reset(ctx, sel.size());
+        dsel.upload(sel.data(), sel.size());
+    }
     out.X = dX.to_host();
     std::vector<int> st = dstate.to_host();
     out.steps.assign(st.begin(), st.begin() + R);
