@@ -353,6 +353,29 @@ def test_function_multiple_entries_local_vs_dense(kr, O, graphs, monkeypatch, gn
     assert np.max(np.abs(Xa - Xb)) <= 1e-12 * scale
 
 
+def test_function_multiple_entries_local_step_limit_goes_dense(kr, O, graphs, monkeypatch):
+    """A space that needs more steps than the one-CTA path carries (24) while the caller allows more is handed to the
+    dense batch: same entries and the same iteration count (30 here) as the dense batch alone and as the oracle."""
+    A = (graphs("transport_Vermont").astype(np.float64) * 6.0).tocsr()
+    nrm, _ = O.normest(A, 1e-2)
+    tol = 1e-10 * float(np.exp(nrm))
+    L = sp.tril(A, -1).tocoo()
+    sel = np.random.default_rng(17).choice(L.nnz, 48, replace=False)
+    om = np.stack([L.row[sel] + 1, L.col[sel] + 1], 1).astype(np.int64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        X1, it1 = kr.function_multiple_entries(A, om, "exp", tol, 100)
+        monkeypatch.setenv("KR_ENTRIES_LOCAL", "0")
+        X0, it0 = kr.function_multiple_entries(A, om, "exp", tol, 100)
+        monkeypatch.delenv("KR_ENTRIES_LOCAL")
+        X6, it6 = kr.function_multiple_entries(A, om[:6], "exp", tol, 100)
+        oX, oit = O.function_multiple_entries(A, om[:6], "exp", tol, 100)
+    assert it1 == it0 and it1 > 24
+    assert it6 == oit
+    assert np.max(np.abs(X1 - X0)) <= 1e-12 * np.max(np.abs(X0))
+    assert np.max(np.abs(X6 - oX)) <= RTOL * np.max(np.abs(oX))
+
+
 def test_function_multiple_entries_local_small_components(kr, O, monkeypatch):
     """Start nodes whose component is exhausted after a few steps (lucky breakdown: the new vector is exactly zero), an
     isolated node, self loops and a pattern-only matrix: the one-CTA path and the dense batch walk through the same
