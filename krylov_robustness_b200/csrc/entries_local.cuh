@@ -37,7 +37,8 @@ struct EntriesLocalArgs {
     int* flag;                       // [R] nonzero = not handled here (1: ball outgrew the budget, 2: step limit of this path)
     int* ticket;
     int R, itl, it_is_cap, fun;      // itl = min(it, EL_IT); it_is_cap: it <= EL_IT (running out of steps is final)
-    int use_ql;                      // projected solve: 1 = tridiagonal QL by one warp, 0 = the dense path's Jacobi
+    int use_ql;                      // projected solve: 2 = scaled Taylor of e^{+-T} e1 by one warp (QL when ||T|| is large),
+                                     // 1 = tridiagonal QL by one warp, 0 = the dense path's Jacobi
     int maxn, hcap, hshift, arena;   // budget (hshift = 32 - log2 hcap)
     const int* sel;                  // columns to process (null: all of 0..R-1)
     int nsel;
@@ -140,6 +141,59 @@ __device__ __forceinline__ void warp_tridiag_fx(const double* H, int it1, int n,
         for (int k = 0; k < n; ++k) sum += Q[lane * EL_LDQ + k] * fun_eval(fun, d[k]) * Q[k];
         x[lane] = sum;
     }
+}
+
+// The same x = f(T) e1 without an eigen-decomposition: f is exp / sinh / cosh, so x comes from y+ = e^{T} e1 and
+// y- = e^{-T} e1, each evaluated as (e^{T/s})^s e1 with s = ceil(||T||_inf) and a degree-20 Taylor polynomial per stage
+// (||T/s|| <= 1: truncation 1/21! = 2e-20, no cancellation; the scheme of expmv.m:62-90 with theta = 1).  Lane i holds
+// component i, a product with the tridiagonal T is two shuffles and three multiply-adds: 20 s short dependent steps
+// instead of the ~2 n^2 dependent rotations of the QL solve.  Returns false (nothing written) when s would exceed
+// EL_TAYLOR_MAX_S; the caller then takes the QL solve.
+constexpr int EL_TAYLOR_MAX_S = 48;
+__device__ __forceinline__ bool warp_tridiag_fx_taylor(const double* H, int it1, int n, int fun, double* x) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const double di = lane < n ? H[(int64_t)lane * (it1 + 1) + lane] : 0.0;
+    const double eu = lane + 1 < n ? 0.5 * (H[(int64_t)lane * (it1 + 1) + lane + 1] + H[(int64_t)(lane + 1) * (it1 + 1) + lane]) : 0.0;
+    double el = __shfl_up_sync(full, eu, 1);
+    if (lane == 0) el = 0.0;
+    double rho = fabs(di) + fabs(eu) + fabs(el);
+    for (int o = 16; o; o >>= 1) rho = fmax(rho, __shfl_xor_sync(full, rho, o));
+    if (!(rho <= (double)EL_TAYLOR_MAX_S)) return false;          // also catches NaN
+    const int ns = rho > 1.0 ? (int)ceil(rho) : 1;
+    const double inv_s = 1.0 / (double)ns;
+    const bool both = fun != KR_FUN_EXP;
+    double yp = lane == 0 ? 1.0 : 0.0, ym = yp;
+    if (ns == 1) {
+        // no scaling: the even / odd terms of the one series are cosh / sinh themselves (no cancellation for small ||T||)
+        double tp = yp, ev = yp, od = 0.0;
+#pragma unroll 4
+        for (int k = 1; k <= 20; ++k) {
+            const double up = __shfl_up_sync(full, tp, 1), dn = __shfl_down_sync(full, tp, 1);
+            tp = (di * tp + el * up + eu * dn) * (1.0 / (double)k);
+            if (k & 1) od += tp; else ev += tp;
+        }
+        if (lane < n) x[lane] = fun == KR_FUN_EXP ? ev + od : fun == KR_FUN_SINH ? od : ev;
+        return true;
+    }
+#pragma unroll 1
+    for (int stage = 0; stage < ns; ++stage) {
+        double tp = yp, tm = ym;
+#pragma unroll 4
+        for (int k = 1; k <= 20; ++k) {
+            const double ck = inv_s / (double)k;
+            const double up = __shfl_up_sync(full, tp, 1), dn = __shfl_down_sync(full, tp, 1);
+            tp = (di * tp + el * up + eu * dn) * ck;
+            yp += tp;
+            if (both) {
+                const double um = __shfl_up_sync(full, tm, 1), dm = __shfl_down_sync(full, tm, 1);
+                tm = -(di * tm + el * um + eu * dm) * ck;
+                ym += tm;
+            }
+        }
+    }
+    if (lane < n) x[lane] = fun == KR_FUN_EXP ? yp : fun == KR_FUN_SINH ? 0.5 * (yp - ym) : 0.5 * (yp + ym);
+    return true;
 }
 
 __global__ void __launch_bounds__(JAC_THREADS)
@@ -301,7 +355,11 @@ entries_local_kernel(CsrDevView A, EntriesLocalArgs a) {
             // ---- projected problem and stopping test
             const int jj = j + 1;
             if (a.use_ql) {
-                if (warp == 0) warp_tridiag_fx(Hl, it1, jj, a.fun, scratch, scratch + a.itl * EL_LDQ);
+                if (warp == 0) {
+                    double* xs = scratch + a.itl * EL_LDQ;
+                    if (a.use_ql != 2 || !warp_tridiag_fx_taylor(Hl, it1, jj, a.fun, xs))
+                        warp_tridiag_fx(Hl, it1, jj, a.fun, scratch, xs);
+                }
                 __syncthreads();
                 done = entries_stop_test(scratch + a.itl * EL_LDQ, it1, jj, a.tol, ring, &sh);
             } else {
@@ -377,8 +435,9 @@ inline EntriesLocalResult entries_local_run(kr_ctx* ctx, const kr_matrix* M, con
     a.it_is_cap = it <= EL_IT;
     a.fun = fun;
     a.tol = tol;
-    a.use_ql = 1;
-    if (const char* e = getenv("KR_ENTRIES_LOCAL_JACOBI")) a.use_ql = atoi(e) == 0;     // A/B switch
+    a.use_ql = 2;
+    if (const char* e = getenv("KR_ENTRIES_LOCAL_SOLVE")) a.use_ql = std::min(std::max(atoi(e), 0), 2);     // A/B switch
+    if (const char* e = getenv("KR_ENTRIES_LOCAL_JACOBI")) if (atoi(e) != 0) a.use_ql = 0;
     static bool attr_set[64] = {};
     if (first_use_on_device(attr_set, ctx->device))
         KR_CUDA(cudaFuncSetAttribute(entries_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
